@@ -1,0 +1,1032 @@
+// OT graph-alignment loss (IPOT) for sm_100a: cost contraction, shared/register-resident solver,
+// gradient contraction.  Reference behaviour: src/clip-event/model_ot.py:8-84 and
+// src/clip-event/model_clip.py:679-715 (see include/clip_event_b200.h for the boundary).
+//
+// Three launches per call, all batched over samples (no cross-sample exchange):
+//   ot_cost_kernel  S[b,n,m] = <y_n, x_m>, |x_m|^2, |y_n|^2      reads x, y once   (HBM-bound)
+//   ot_ipot_kernel  C = 1 - S/(|x||y|); T = IPOT(C); dist; W, ax, ay   (on-chip, ALU-bound)
+//   ot_grad_kernel  dx = -W y + ax*x ; dy = -W^t x + ay*y          reads x, y, writes dx, dy
+// where W[m,n] = scale * T[n,m] / (|x_m||y_n|) and ax, ay carry the normalisation backward
+// (d x^ = -dC y^,  dx = (dx^ - x^ (x^.dx^)) / |x|,  x^.dx^ = -sum_n dC[m,n] S^[m,n]).
+// The contractions run on the tensor cores through warp-level mma (tf32, 3-way split in fp32
+// mode so the cost matrix keeps fp32 accuracy: IPOT amplifies cost error by iters/beta).
+#include "ce_common.cuh"
+
+namespace ce {
+namespace {
+
+constexpr int kDC = 32;        // embedding columns staged per step
+constexpr int kLdA = kDC + 4;  // smem row stride (floats) for operands read along K  (== 4 mod 32)
+constexpr int kLdB = kDC + 8;  // smem row stride for operands read across K          (== 8 mod 32)
+
+struct OtArgs {
+  const void* txt;
+  const void* img;
+  int64_t txt_bs, img_bs;  // sample strides in elements
+  int B, M, N, D;
+  int tiles_per_cta;       // 16-row tiles of image nodes handled by one CTA
+  float* S;                // [B, N, MP]  raw dots, later W
+  float* nx2;              // [B, MP]     |x|^2, later ax
+  float* ny2;              // [B, Nld]    |y|^2, later ay
+  int Nld;
+  void* dtxt;
+  void* dimg;
+  float* dx_acc;           // [B, M, D] fp32, only when a sample is split over several CTAs
+  int nsplit;
+};
+
+template <int NSPLIT>
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = f2tf32(v);
+  if constexpr (NSPLIT == 3) lo = f2tf32(v - __uint_as_float(hi));
+  else lo = 0;
+}
+
+// acc += A*B with the configured number of tf32 products (small cross terms first).
+template <int NSPLIT>
+__device__ __forceinline__ void mma_split(float* acc, const uint32_t* ahi, const uint32_t* alo,
+                                          const uint32_t* bhi, const uint32_t* blo) {
+  if constexpr (NSPLIT == 3) {
+    mma_tf32(acc, alo, bhi);
+    mma_tf32(acc, ahi, blo);
+  }
+  mma_tf32(acc, ahi, bhi);
+}
+
+// Stage `rows` rows x kDC columns (starting at column d0) of a [*, D] matrix into smem as fp32.
+template <int DT, int LD>
+__device__ __forceinline__ void stage_rows(float* dst, const typename In<DT>::type* src, int rows,
+                                           int rows_valid, int D, int d0, int nthreads) {
+  constexpr int V = In<DT>::kVec;
+  constexpr int G = kDC / V;  // 16-byte groups per row
+  for (int idx = threadIdx.x; idx < rows * G; idx += nthreads) {
+    int r = idx / G, c = (idx % G) * V;
+    float v[8];
+    if (r < rows_valid && d0 + c < D) {
+      In<DT>::load16(src + (int64_t)r * D + d0 + c, v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = 0.f;
+    }
+    float4* p = reinterpret_cast<float4*>(dst + r * LD + c);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    if constexpr (V == 8) p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel A: S = y x^t (raw), row sums of squares.
+// grid (B, nsplit); CTA handles image-node tiles [ns*tiles_per_cta, ...); warp w owns tiles
+// w, w+NWARPS, ...; text nodes (padded to MP) sit on the mma N axis.
+// ------------------------------------------------------------------------------------------
+template <int DT, int MP, int NWARPS, int TPW>
+__global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
+  constexpr int NSPLIT = (DT == CE_F32) ? 3 : 1;
+  constexpr int NT = NWARPS * 32;
+  constexpr int NJ = MP / 8;
+  using T = typename In<DT>::type;
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.x, ns = blockIdx.y;
+  const int ntiles = (a.N + 15) / 16;
+  const int tile0 = ns * a.tiles_per_cta;
+  const int my_tiles = min(a.tiles_per_cta, ntiles - tile0);
+  const int row0 = tile0 * 16;
+  const int rows = my_tiles * 16;
+  const int rows_valid = min(rows, a.N - row0);
+  float* xs = smem;             // [MP][kLdA]
+  float* ys = smem + MP * kLdA; // [rows][kLdA]
+  const T* xg = reinterpret_cast<const T*>(a.txt) + (int64_t)b * a.txt_bs;
+  const T* yg = reinterpret_cast<const T*>(a.img) + (int64_t)b * a.img_bs + (int64_t)row0 * a.D;
+  const int w = warp_id(), lane = lane_id(), g = lane >> 2, t = lane & 3;
+
+  float acc[TPW][NJ][4];
+  float yss[TPW][2];
+  float xss[NJ];
+#pragma unroll
+  for (int i = 0; i < TPW; ++i) {
+    yss[i][0] = yss[i][1] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) xss[j] = 0.f;
+
+  for (int d0 = 0; d0 < a.D; d0 += kDC) {
+    stage_rows<DT, kLdA>(xs, xg, MP, a.M, a.D, d0, NT);
+    stage_rows<DT, kLdA>(ys, yg, rows, rows_valid, a.D, d0, NT);
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < kDC / 8; ++ks) {
+      uint32_t bhi[NJ][2], blo[NJ][2];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float b0 = xs[(8 * j + g) * kLdA + ks * 8 + t];
+        float b1 = xs[(8 * j + g) * kLdA + ks * 8 + t + 4];
+        xss[j] += b0 * b0 + b1 * b1;
+        split_tf32<NSPLIT>(b0, bhi[j][0], blo[j][0]);
+        split_tf32<NSPLIT>(b1, bhi[j][1], blo[j][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < TPW; ++i) {
+        int tile = w + i * NWARPS;
+        if (tile < my_tiles) {
+          const float* yr = ys + (tile * 16 + g) * kLdA + ks * 8 + t;
+          float av[4] = {yr[0], yr[8 * kLdA], yr[4], yr[8 * kLdA + 4]};
+          yss[i][0] += av[0] * av[0] + av[2] * av[2];
+          yss[i][1] += av[1] * av[1] + av[3] * av[3];
+          uint32_t ahi[4], alo[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) split_tf32<NSPLIT>(av[c], ahi[c], alo[c]);
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) mma_split<NSPLIT>(acc[i][j], ahi, alo, bhi[j], blo[j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  float* Sg = a.S + ((int64_t)b * a.N + row0) * MP;
+#pragma unroll
+  for (int i = 0; i < TPW; ++i) {
+    int tile = w + i * NWARPS;
+    if (tile < my_tiles) {
+      int r = tile * 16 + g;
+      float s0 = yss[i][0], s1 = yss[i][1];
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      if (t == 0) {
+        if (r < rows_valid) a.ny2[(int64_t)b * a.Nld + row0 + r] = s0;
+        if (r + 8 < rows_valid) a.ny2[(int64_t)b * a.Nld + row0 + r + 8] = s1;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        int m = 8 * j + 2 * t;
+        if (r < rows_valid)
+          *reinterpret_cast<float2*>(Sg + (int64_t)r * MP + m) = make_float2(acc[i][j][0], acc[i][j][1]);
+        if (r + 8 < rows_valid)
+          *reinterpret_cast<float2*>(Sg + (int64_t)(r + 8) * MP + m) =
+              make_float2(acc[i][j][2], acc[i][j][3]);
+      }
+    }
+  }
+  if (ns == 0 && w == 0) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float v = xss[j];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (t == 0) a.nx2[(int64_t)b * MP + 8 * j + g] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel B: IPOT on one sample per CTA, plan and kernel matrix resident in registers.
+// Thread layout: TC = MP/4 threads across a row (4 consecutive text nodes each), 256/TC image
+// rows per pass, RPT passes.  Row sums: in-thread + log2(TC) shuffles.  Column sums: in-thread
+// over RPT rows, shuffles over the rows of a warp, one smem exchange across warps.
+// ------------------------------------------------------------------------------------------
+struct IpotArgs {
+  float* S;         // in: raw dots [B,N,MP]; out: W
+  float* nx2;       // in: |x|^2 [B,MP];  out: ax
+  float* ny2;       // in: |y|^2 [B,Nld]; out: ay
+  const void* txt_mask;
+  const void* img_mask;
+  int64_t txt_ms, img_ms;
+  int mask_kind;
+  int B, M, N, Nld;
+  float beta, eps, scale;
+  int iters, k;
+  float* dist;      // [B]
+};
+
+__device__ __forceinline__ bool node_is_pad(const void* mask, int kind, int64_t idx) {
+  if (kind == CE_MASK_NUM_I64) return reinterpret_cast<const int64_t*>(mask)[idx] == 0;
+  return reinterpret_cast<const uint8_t*>(mask)[idx] != 0;
+}
+
+template <int MP, int RPT>
+__global__ void __launch_bounds__(256) ot_ipot_kernel(IpotArgs a) {
+  constexpr int TC = MP / 4;       // threads per row
+  constexpr int RP = 256 / TC;     // rows per pass
+  constexpr int RW = 32 / TC;      // rows per warp per pass
+  __shared__ float s_rx[MP], s_sigma[MP], s_xguard[MP];
+  __shared__ float s_red[8][MP];
+  __shared__ float s_cnt[2];
+  __shared__ float s_red2[8];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int tc = tid % TC, tr = tid / TC;
+  const int m0 = tc * 4;
+
+  // ---- masks, lengths, norms --------------------------------------------------------------
+  if (tid < MP) {
+    bool pad = tid >= a.M || node_is_pad(a.txt_mask, a.mask_kind, (int64_t)b * a.txt_ms + tid);
+    float n2 = a.nx2[(int64_t)b * MP + tid];
+    s_rx[tid] = 1.f / fmaxf(sqrtf(n2), a.eps);
+    s_xguard[tid] = pad ? 1e4f : 0.f;
+  }
+  if (tid < 2) s_cnt[tid] = 0.f;
+  __syncthreads();
+  float ry[RPT], yguard[RPT];
+  {
+    float cnt = 0.f;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      int n = tr + i * RP;
+      bool pad = n >= a.N || node_is_pad(a.img_mask, a.mask_kind, (int64_t)b * a.img_ms + n);
+      float n2 = n < a.N ? a.ny2[(int64_t)b * a.Nld + n] : 1.f;
+      ry[i] = 1.f / fmaxf(sqrtf(n2), a.eps);
+      yguard[i] = pad ? 1e4f : 0.f;
+      if (tc == 0 && !pad) cnt += 1.f;
+    }
+    cnt = warp_sum(cnt);
+    if (lane == 0 && cnt != 0.f) atomicAdd(&s_cnt[1], cnt);
+    if (tid < MP && s_xguard[tid] == 0.f) atomicAdd(&s_cnt[0], 1.f);
+  }
+  __syncthreads();
+  const float xlen = s_cnt[0], ylen = s_cnt[1];
+  float* Sg = a.S + (int64_t)b * a.N * MP;
+
+  if (xlen == 0.f || ylen == 0.f) {
+    // model_ot.py:62 -- the final mask zeroes the whole plan: distance 0, gradient 0
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      int n = tr + i * RP;
+      if (n < a.N) {
+        *reinterpret_cast<float4*>(Sg + (int64_t)n * MP + m0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tc == 0) a.ny2[(int64_t)b * a.Nld + n] = 0.f;
+      }
+    }
+    if (tid < MP) a.nx2[(int64_t)b * MP + tid] = 0.f;
+    if (tid == 0) a.dist[b] = 0.f;
+    return;
+  }
+
+  // ---- kernel matrix A = exp(-C/beta), plan T = 1 (0 at joint pads) -----------------------
+  float A[RPT][4], T[RPT][4];
+  float rx[4], xg[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { rx[j] = s_rx[m0 + j]; xg[j] = s_xguard[m0 + j]; }
+  const float nib = -1.f / a.beta;
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    int n = tr + i * RP;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < a.N) s4 = *reinterpret_cast<const float4*>(Sg + (int64_t)n * MP + m0);
+    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bool valid = yguard[i] == 0.f && xg[j] == 0.f;
+      float c = 1.f - sv[j] * rx[j] * ry[i];
+      A[i][j] = valid ? expf(c * nib) : 0.f;
+      T[i][j] = valid ? 1.f : 0.f;
+    }
+  }
+  if (tid < MP) s_sigma[tid] = s_xguard[tid] == 0.f ? 1.f / xlen : 0.f;
+  __syncthreads();
+
+  // ---- IPOT iterations (model_ot.py:55-61) -------------------------------------------------
+  float sig[4];
+  for (int it = 0; it < a.iters; ++it) {
+    float delta[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) T[i][j] *= A[i][j];  // Q = A * T
+    for (int kk = 0; kk < a.k; ++kk) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sig[j] = s_sigma[m0 + j];
+      float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        float rs = T[i][0] * sig[0] + T[i][1] * sig[1] + T[i][2] * sig[2] + T[i][3] * sig[3];
+#pragma unroll
+        for (int o = 1; o < TC; o <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+        float d = 1.f / (ylen * rs + yguard[i]);
+        delta[i] = d;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cs[j] += d * T[i][j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int o = TC; o < 32; o <<= 1) cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], o);
+      }
+      __syncthreads();  // everyone has read s_sigma
+      if (lane < TC) *reinterpret_cast<float4*>(&s_red[w][m0]) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+      __syncthreads();
+      if (tid < MP) {
+        float v = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) v += s_red[ww][tid];
+        s_sigma[tid] = 1.f / (xlen * v + s_xguard[tid]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sig[j] = s_sigma[m0 + j];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) T[i][j] = delta[i] * T[i][j] * sig[j];
+  }
+  (void)RW;
+
+  // ---- distance, W, normalisation-backward coefficients -----------------------------------
+  float dsum = 0.f;
+  float px[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    int n = tr + i * RP;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < a.N) s4 = *reinterpret_cast<const float4*>(Sg + (int64_t)n * MP + m0);
+    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+    float py = 0.f, wv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bool valid = yguard[i] == 0.f && xg[j] == 0.f;
+      float shat = sv[j] * rx[j] * ry[i];
+      float tt = valid ? T[i][j] : 0.f;  // model_ot.py:62 final mask (also drops NaNs at pads)
+      dsum += (1.f - shat) * tt;
+      float tg = a.scale * tt;
+      px[j] += tg * shat;
+      py += tg * shat;
+      wv[j] = tg * rx[j] * ry[i];
+    }
+#pragma unroll
+    for (int o = 1; o < TC; o <<= 1) py += __shfl_xor_sync(0xffffffffu, py, o);
+    if (n < a.N) {
+      *reinterpret_cast<float4*>(Sg + (int64_t)n * MP + m0) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+      if (tc == 0) {
+        float n2 = a.ny2[(int64_t)b * a.Nld + n];
+        // |y| < eps: F.normalize divides by eps and the projection term has no gradient
+        a.ny2[(int64_t)b * a.Nld + n] = (sqrtf(n2) >= a.eps) ? py * ry[i] * ry[i] : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int o = TC; o < 32; o <<= 1) px[j] += __shfl_xor_sync(0xffffffffu, px[j], o);
+  }
+  dsum = warp_sum(dsum);
+  __syncthreads();
+  if (lane < TC) *reinterpret_cast<float4*>(&s_red[w][m0]) = make_float4(px[0], px[1], px[2], px[3]);
+  if (lane == 0) s_red2[w] = dsum;
+  __syncthreads();
+  if (tid < MP) {
+    float v = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) v += s_red[ww][tid];
+    float n2 = a.nx2[(int64_t)b * MP + tid];
+    float r = s_rx[tid];
+    a.nx2[(int64_t)b * MP + tid] = (sqrtf(n2) >= a.eps) ? v * r * r : 0.f;
+  }
+  if (tid == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) v += s_red2[ww];
+    a.dist[b] = v;
+  }
+}
+
+// Fallback solver for shapes whose plan does not fit the register-resident kernel: same maths,
+// kernel matrix and plan live in a global scratch (L2-resident), one CTA per sample.
+struct IpotBigArgs {
+  IpotArgs a;
+  float* scratch;  // [B, 2, N, MP]
+  int MP;
+};
+__global__ void __launch_bounds__(256) ot_ipot_big_kernel(IpotBigArgs p) {
+  const IpotArgs& a = p.a;
+  const int MP = p.MP, b = blockIdx.x, tid = threadIdx.x;
+  extern __shared__ float sm[];
+  float* s_rx = sm;                 // MP
+  float* s_sigma = s_rx + MP;       // MP
+  float* s_xg = s_sigma + MP;       // MP
+  float* s_col = s_xg + MP;         // MP
+  float* s_ry = s_col + MP;         // N
+  float* s_yg = s_ry + a.N;         // N
+  float* s_delta = s_yg + a.N;      // N
+  __shared__ float s_cnt[2];
+  __shared__ float s_dsum;
+  if (tid < 2) s_cnt[tid] = 0.f;
+  if (tid == 0) s_dsum = 0.f;
+  __syncthreads();
+  for (int m = tid; m < MP; m += 256) {
+    bool pad = m >= a.M || node_is_pad(a.txt_mask, a.mask_kind, (int64_t)b * a.txt_ms + m);
+    s_rx[m] = 1.f / fmaxf(sqrtf(a.nx2[(int64_t)b * MP + m]), a.eps);
+    s_xg[m] = pad ? 1e4f : 0.f;
+    if (!pad) atomicAdd(&s_cnt[0], 1.f);
+  }
+  for (int n = tid; n < a.N; n += 256) {
+    bool pad = node_is_pad(a.img_mask, a.mask_kind, (int64_t)b * a.img_ms + n);
+    s_ry[n] = 1.f / fmaxf(sqrtf(a.ny2[(int64_t)b * a.Nld + n]), a.eps);
+    s_yg[n] = pad ? 1e4f : 0.f;
+    if (!pad) atomicAdd(&s_cnt[1], 1.f);
+  }
+  __syncthreads();
+  const float xlen = s_cnt[0], ylen = s_cnt[1];
+  float* Sg = a.S + (int64_t)b * a.N * MP;
+  float* Ag = p.scratch + (int64_t)b * 2 * a.N * MP;
+  float* Tg = Ag + (int64_t)a.N * MP;
+  const int E = a.N * MP;
+  if (xlen == 0.f || ylen == 0.f) {
+    for (int e = tid; e < E; e += 256) Sg[e] = 0.f;
+    for (int n = tid; n < a.N; n += 256) a.ny2[(int64_t)b * a.Nld + n] = 0.f;
+    for (int m = tid; m < MP; m += 256) a.nx2[(int64_t)b * MP + m] = 0.f;
+    if (tid == 0) a.dist[b] = 0.f;
+    return;
+  }
+  const float nib = -1.f / a.beta;
+  for (int e = tid; e < E; e += 256) {
+    int n = e / MP, m = e % MP;
+    bool valid = s_yg[n] == 0.f && s_xg[m] == 0.f;
+    float c = 1.f - Sg[e] * s_rx[m] * s_ry[n];
+    Ag[e] = valid ? expf(c * nib) : 0.f;
+    Tg[e] = valid ? 1.f : 0.f;
+  }
+  for (int m = tid; m < MP; m += 256) s_sigma[m] = s_xg[m] == 0.f ? 1.f / xlen : 0.f;
+  __syncthreads();
+  const int w = tid >> 5, lane = tid & 31;
+  for (int it = 0; it < a.iters; ++it) {
+    for (int e = tid; e < E; e += 256) Tg[e] *= Ag[e];
+    __syncthreads();
+    for (int kk = 0; kk < a.k; ++kk) {
+      for (int n = w; n < a.N; n += 8) {
+        float rs = 0.f;
+        for (int m = lane; m < MP; m += 32) rs += Tg[n * MP + m] * s_sigma[m];
+        rs = warp_sum(rs);
+        if (lane == 0) s_delta[n] = 1.f / (ylen * rs + s_yg[n]);
+      }
+      __syncthreads();
+      for (int m = w; m < MP; m += 8) {
+        float cs = 0.f;
+        for (int n = lane; n < a.N; n += 32) cs += s_delta[n] * Tg[n * MP + m];
+        cs = warp_sum(cs);
+        if (lane == 0) s_sigma[m] = 1.f / (xlen * cs + s_xg[m]);
+      }
+      __syncthreads();
+    }
+    for (int e = tid; e < E; e += 256) {
+      int n = e / MP, m = e % MP;
+      Tg[e] = s_delta[n] * Tg[e] * s_sigma[m];
+    }
+    __syncthreads();
+  }
+  for (int m = tid; m < MP; m += 256) s_col[m] = 0.f;
+  for (int n = tid; n < a.N; n += 256) s_delta[n] = 0.f;
+  __syncthreads();
+  float dsum = 0.f;
+  for (int e = tid; e < E; e += 256) {
+    int n = e / MP, m = e % MP;
+    bool valid = s_yg[n] == 0.f && s_xg[m] == 0.f;
+    float shat = Sg[e] * s_rx[m] * s_ry[n];
+    float tt = valid ? Tg[e] : 0.f;
+    dsum += (1.f - shat) * tt;
+    float tg = a.scale * tt;
+    atomicAdd(&s_col[m], tg * shat);
+    atomicAdd(&s_delta[n], tg * shat);
+    Sg[e] = tg * s_rx[m] * s_ry[n];
+  }
+  dsum = warp_sum(dsum);
+  if (lane == 0) atomicAdd(&s_dsum, dsum);
+  __syncthreads();
+  for (int m = tid; m < MP; m += 256) {
+    float n2 = a.nx2[(int64_t)b * MP + m];
+    a.nx2[(int64_t)b * MP + m] = (sqrtf(n2) >= a.eps) ? s_col[m] * s_rx[m] * s_rx[m] : 0.f;
+  }
+  for (int n = tid; n < a.N; n += 256) {
+    float n2 = a.ny2[(int64_t)b * a.Nld + n];
+    a.ny2[(int64_t)b * a.Nld + n] = (sqrtf(n2) >= a.eps) ? s_delta[n] * s_ry[n] * s_ry[n] : 0.f;
+  }
+  if (tid == 0) a.dist[b] = s_dsum;
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel C: dy = -W^t x + ay*y (rows of this CTA), dx = -W y + ax*x (partial over its rows).
+// ------------------------------------------------------------------------------------------
+template <int DT>
+__device__ __forceinline__ void store2(typename In<DT>::type* p, float v0, float v1) {
+  if constexpr (DT == CE_F32) {
+    *reinterpret_cast<float2*>(p) = make_float2(v0, v1);
+  } else {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v0, v1);
+  }
+}
+
+template <int DT, int MP, int NWARPS, int TPW>
+__global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
+  constexpr int NSPLIT = (DT == CE_F32) ? 3 : 1;
+  constexpr int NT = NWARPS * 32;
+  constexpr int LDW = MP + 4;
+  constexpr int NOUT = (MP / 16) * (kDC / 8);            // dx output tiles per step
+  constexpr int OPW = (NOUT + NWARPS - 1) / NWARPS;      // per warp
+  using T = typename In<DT>::type;
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.x, ns = blockIdx.y;
+  const int ntiles = (a.N + 15) / 16;
+  const int tile0 = ns * a.tiles_per_cta;
+  const int my_tiles = min(a.tiles_per_cta, ntiles - tile0);
+  const int row0 = tile0 * 16;
+  const int rows = my_tiles * 16;
+  const int rows_valid = min(rows, a.N - row0);
+  float* xs = smem;                       // [MP][kLdB]
+  float* ys = xs + MP * kLdB;             // [rows][kLdB]
+  float* Ws = ys + rows * kLdB;           // [rows][LDW]
+  float* axs = Ws + rows * LDW;           // [MP]
+  float* ays = axs + MP;                  // [rows]
+  const T* xg = reinterpret_cast<const T*>(a.txt) + (int64_t)b * a.txt_bs;
+  const T* yg = reinterpret_cast<const T*>(a.img) + (int64_t)b * a.img_bs + (int64_t)row0 * a.D;
+  T* dxg = reinterpret_cast<T*>(a.dtxt) + (int64_t)b * a.txt_bs;
+  T* dyg = reinterpret_cast<T*>(a.dimg) + (int64_t)b * a.img_bs + (int64_t)row0 * a.D;
+  const int w = warp_id(), lane = lane_id(), g = lane >> 2, t = lane & 3;
+
+  {  // W, ax, ay for this CTA's rows
+    const float* Wg = a.S + ((int64_t)b * a.N + row0) * MP;
+    for (int idx = threadIdx.x; idx < rows * (MP / 4); idx += NT) {
+      int r = idx / (MP / 4), c = (idx % (MP / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows_valid) v = *reinterpret_cast<const float4*>(Wg + (int64_t)r * MP + c);
+      *reinterpret_cast<float4*>(Ws + r * LDW + c) = v;
+    }
+    for (int m = threadIdx.x; m < MP; m += NT) axs[m] = a.nx2[(int64_t)b * MP + m];
+    for (int r = threadIdx.x; r < rows; r += NT)
+      ays[r] = r < rows_valid ? a.ny2[(int64_t)b * a.Nld + row0 + r] : 0.f;
+  }
+
+  for (int d0 = 0; d0 < a.D; d0 += kDC) {
+    __syncthreads();
+    stage_rows<DT, kLdB>(xs, xg, MP, a.M, a.D, d0, NT);
+    stage_rows<DT, kLdB>(ys, yg, rows, rows_valid, a.D, d0, NT);
+    __syncthreads();
+
+    // ---- dy tiles: rows of this warp, K = text nodes -------------------------------------
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+      int tile = w + i * NWARPS;
+      if (tile < my_tiles) {
+        float acc[kDC / 8][4];
+#pragma unroll
+        for (int j = 0; j < kDC / 8; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < MP / 8; ++ks) {
+          const float* wr = Ws + (tile * 16 + g) * LDW + ks * 8 + t;
+          uint32_t ahi[4], alo[4];
+          split_tf32<NSPLIT>(wr[0], ahi[0], alo[0]);
+          split_tf32<NSPLIT>(wr[8 * LDW], ahi[1], alo[1]);
+          split_tf32<NSPLIT>(wr[4], ahi[2], alo[2]);
+          split_tf32<NSPLIT>(wr[8 * LDW + 4], ahi[3], alo[3]);
+#pragma unroll
+          for (int j = 0; j < kDC / 8; ++j) {
+            uint32_t bhi[2], blo[2];
+            split_tf32<NSPLIT>(xs[(ks * 8 + t) * kLdB + 8 * j + g], bhi[0], blo[0]);
+            split_tf32<NSPLIT>(xs[(ks * 8 + t + 4) * kLdB + 8 * j + g], bhi[1], blo[1]);
+            mma_split<NSPLIT>(acc[j], ahi, alo, bhi, blo);
+          }
+        }
+        int r = tile * 16 + g;
+#pragma unroll
+        for (int j = 0; j < kDC / 8; ++j) {
+          int d = 8 * j + 2 * t;
+          if (d0 + d < a.D) {
+            if (r < rows_valid) {
+              float ay = ays[r];
+              store2<DT>(dyg + (int64_t)r * a.D + d0 + d, ay * ys[r * kLdB + d] - acc[j][0],
+                         ay * ys[r * kLdB + d + 1] - acc[j][1]);
+            }
+            if (r + 8 < rows_valid) {
+              float ay = ays[r + 8];
+              store2<DT>(dyg + (int64_t)(r + 8) * a.D + d0 + d,
+                         ay * ys[(r + 8) * kLdB + d] - acc[j][2],
+                         ay * ys[(r + 8) * kLdB + d + 1] - acc[j][3]);
+            }
+          }
+        }
+      }
+    }
+
+    // ---- dx tiles: outputs split over warps, K = this CTA's image rows --------------------
+#pragma unroll
+    for (int o = 0; o < OPW; ++o) {
+      int ot = w + o * NWARPS;
+      if (ot < NOUT) {
+        int mi = ot / (kDC / 8), j = ot % (kDC / 8);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int ks = 0; ks < rows / 8; ++ks) {
+          const float* wr = Ws + (ks * 8 + t) * LDW + 16 * mi + g;
+          uint32_t ahi[4], alo[4];
+          split_tf32<NSPLIT>(wr[0], ahi[0], alo[0]);
+          split_tf32<NSPLIT>(wr[8], ahi[1], alo[1]);
+          split_tf32<NSPLIT>(wr[4 * LDW], ahi[2], alo[2]);
+          split_tf32<NSPLIT>(wr[4 * LDW + 8], ahi[3], alo[3]);
+          uint32_t bhi[2], blo[2];
+          split_tf32<NSPLIT>(ys[(ks * 8 + t) * kLdB + 8 * j + g], bhi[0], blo[0]);
+          split_tf32<NSPLIT>(ys[(ks * 8 + t + 4) * kLdB + 8 * j + g], bhi[1], blo[1]);
+          mma_split<NSPLIT>(acc, ahi, alo, bhi, blo);
+        }
+        int m = 16 * mi + g, d = 8 * j + 2 * t;
+        if (d0 + d < a.D) {
+          if (a.nsplit == 1) {
+            if (m < a.M)
+              store2<DT>(dxg + (int64_t)m * a.D + d0 + d, axs[m] * xs[m * kLdB + d] - acc[0],
+                         axs[m] * xs[m * kLdB + d + 1] - acc[1]);
+            if (m + 8 < a.M)
+              store2<DT>(dxg + (int64_t)(m + 8) * a.D + d0 + d,
+                         axs[m + 8] * xs[(m + 8) * kLdB + d] - acc[2],
+                         axs[m + 8] * xs[(m + 8) * kLdB + d + 1] - acc[3]);
+          } else {
+            float* dacc = a.dx_acc + ((int64_t)b * a.M) * a.D + d0 + d;
+            if (m < a.M) {
+              atomicAdd(dacc + (int64_t)m * a.D, -acc[0]);
+              atomicAdd(dacc + (int64_t)m * a.D + 1, -acc[1]);
+            }
+            if (m + 8 < a.M) {
+              atomicAdd(dacc + (int64_t)(m + 8) * a.D, -acc[2]);
+              atomicAdd(dacc + (int64_t)(m + 8) * a.D + 1, -acc[3]);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// dx = dx_acc + ax * x for samples that were split over several CTAs.
+template <int DT>
+__global__ void ot_dx_finish_kernel(OtArgs a, int MP) {
+  using T = typename In<DT>::type;
+  int64_t total = (int64_t)a.B * a.M * a.D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int d = (int)(i % a.D);
+    int m = (int)((i / a.D) % a.M);
+    int b = (int)(i / ((int64_t)a.D * a.M));
+    const T* xg = reinterpret_cast<const T*>(a.txt) + (int64_t)b * a.txt_bs;
+    T* dxg = reinterpret_cast<T*>(a.dtxt) + (int64_t)b * a.txt_bs;
+    float v = a.dx_acc[i] + a.nx2[(int64_t)b * MP + m] * In<DT>::ld(xg + (int64_t)m * a.D + d);
+    In<DT>::st(dxg + (int64_t)m * a.D + d, v);
+  }
+}
+
+// loss = scale * sum_b dist[b] (left to right like the reference's Python sum, model_clip.py:707),
+// and zero-fill of the dropped whole-image slot's gradient.
+template <int DT>
+__global__ void ot_tail_kernel(const float* dist, int B, float scale, float* loss, void* slot0,
+                               int64_t bs, int D) {
+  using T = typename In<DT>::type;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss != nullptr) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dist[b];
+    *loss = s * scale;
+  }
+  if (slot0 != nullptr) {
+    int64_t total = (int64_t)B * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      int b = (int)(i / D), d = (int)(i % D);
+      In<DT>::st(reinterpret_cast<T*>(slot0) + (int64_t)b * bs + d, 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Building blocks with the reference's granularity (plain SIMT; not on the fused path)
+// ------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void ot_cost_matrix_kernel(const void* x, const void* y, int B, int M, int N, int D,
+                                      float eps, float* cost) {
+  // one warp per (b, m, n) triple
+  using T = typename In<DT>::type;
+  int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int64_t total = (int64_t)B * M * N;
+  if (gw >= total) return;
+  int n = (int)(gw % N), m = (int)((gw / N) % M), b = (int)(gw / ((int64_t)N * M));
+  const T* xr = reinterpret_cast<const T*>(x) + ((int64_t)b * M + m) * D;
+  const T* yr = reinterpret_cast<const T*>(y) + ((int64_t)b * N + n) * D;
+  float dot = 0.f, xx = 0.f, yy = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float xv = In<DT>::ld(xr + d), yv = In<DT>::ld(yr + d);
+    dot += xv * yv; xx += xv * xv; yy += yv * yv;
+  }
+  dot = warp_sum(dot); xx = warp_sum(xx); yy = warp_sum(yy);
+  if (lane == 0) cost[gw] = 1.f - dot / (fmaxf(sqrtf(xx), eps) * fmaxf(sqrtf(yy), eps));
+}
+
+__global__ void ot_trace_kernel(const float* x, int B, int n, float* out) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += x[((int64_t)b * n + i) * n + i];
+  out[b] = s;
+}
+
+// ipot() with the reference's signature: C [B,M,N] (already masked) -> T [B,N,M].
+__global__ void __launch_bounds__(256) ot_ipot_plain_kernel(const float* cost, const uint8_t* xpad,
+                                                            const uint8_t* ypad, int B, int M, int N,
+                                                            float beta, int iters, int k,
+                                                            float* plan) {
+  extern __shared__ float sm[];
+  float* sigma = sm;          // M
+  float* delta = sigma + M;   // N
+  float* xg = delta + N;      // M
+  float* yg = xg + M;         // N
+  __shared__ float cnt[2];
+  const int b = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  if (tid < 2) cnt[tid] = 0.f;
+  __syncthreads();
+  for (int m = tid; m < M; m += 256) { bool p = xpad[(int64_t)b * M + m]; xg[m] = p ? 1e4f : 0.f; if (!p) atomicAdd(&cnt[0], 1.f); }
+  for (int n = tid; n < N; n += 256) { bool p = ypad[(int64_t)b * N + n]; yg[n] = p ? 1e4f : 0.f; if (!p) atomicAdd(&cnt[1], 1.f); }
+  __syncthreads();
+  const float xlen = cnt[0], ylen = cnt[1];
+  const float* C = cost + (int64_t)b * M * N;
+  float* T = plan + (int64_t)b * N * M;   // [N, M]; holds Q during an iteration
+  for (int e = tid; e < N * M; e += 256) {
+    int n = e / M, m = e % M;
+    T[e] = (xg[m] == 0.f && yg[n] == 0.f) ? 1.f : 0.f;
+  }
+  for (int m = tid; m < M; m += 256) sigma[m] = xg[m] == 0.f ? 1.f / xlen : 0.f;
+  __syncthreads();
+  for (int it = 0; it < iters; ++it) {
+    for (int e = tid; e < N * M; e += 256) {
+      int n = e / M, m = e % M;
+      float a = (xg[m] == 0.f && yg[n] == 0.f) ? expf(-C[(int64_t)m * N + n] / beta) : 0.f;
+      T[e] *= a;
+    }
+    __syncthreads();
+    for (int kk = 0; kk < k; ++kk) {
+      for (int n = w; n < N; n += 8) {
+        float rs = 0.f;
+        for (int m = lane; m < M; m += 32) rs += T[n * M + m] * sigma[m];
+        rs = warp_sum(rs);
+        if (lane == 0) delta[n] = 1.f / (ylen * rs + yg[n]);
+      }
+      __syncthreads();
+      for (int m = w; m < M; m += 8) {
+        float cs = 0.f;
+        for (int n = lane; n < N; n += 32) cs += delta[n] * T[n * M + m];
+        cs = warp_sum(cs);
+        if (lane == 0) sigma[m] = 1.f / (xlen * cs + xg[m]);
+      }
+      __syncthreads();
+    }
+    for (int e = tid; e < N * M; e += 256) {
+      int n = e / M, m = e % M;
+      T[e] = delta[n] * T[e] * sigma[m];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < N * M; e += 256) {
+    int n = e / M, m = e % M;
+    if (!(xg[m] == 0.f && yg[n] == 0.f)) T[e] = 0.f;
+  }
+}
+
+template <int DT>
+__global__ void scale_inplace_kernel(void* x, int64_t rows, int64_t row_len, int64_t row_stride,
+                                     const float* g) {
+  using T = typename In<DT>::type;
+  const float s = *g;
+  if (s == 1.f) return;
+  int64_t total = rows * row_len;
+  T* p = reinterpret_cast<T*>(x);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / row_len, c = i % row_len;
+    T* q = p + r * row_stride + c;
+    In<DT>::st(q, In<DT>::ld(q) * s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host dispatch
+// ------------------------------------------------------------------------------------------
+struct OtPlan {
+  int MP, nwarps, tpw, tiles_per_cta, nsplit, rpt;
+  size_t smem_cost, smem_grad;
+};
+
+int make_plan(int M, int N, OtPlan* p) {
+  if (M < 1 || M > 64) return fail(CE_ERR_SHAPE, "OT: text nodes M=%d outside 1..64", M);
+  if (N < 1 || N > 1024) return fail(CE_ERR_SHAPE, "OT: image nodes N=%d outside 1..1024", N);
+  p->MP = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
+  int ntiles = (N + 15) / 16;
+  if (ntiles <= 4) { p->nwarps = 4; p->tpw = 1; }
+  else { p->nwarps = 8; p->tpw = p->MP == 64 ? 2 : 3; }
+  int cap = p->nwarps * p->tpw;
+  p->nsplit = (ntiles + cap - 1) / cap;
+  p->tiles_per_cta = (ntiles + p->nsplit - 1) / p->nsplit;
+  int rows = p->tiles_per_cta * 16;
+  p->smem_cost = sizeof(float) * ((size_t)p->MP * kLdA + (size_t)rows * kLdA);
+  p->smem_grad = sizeof(float) * ((size_t)p->MP * kLdB + (size_t)rows * kLdB +
+                                  (size_t)rows * (p->MP + 4) + p->MP + rows);
+  int rp = 256 / (p->MP / 4);
+  p->rpt = (N + rp - 1) / rp;
+  return CE_OK;
+}
+
+template <int DT, int MP, int NW, int TPW>
+int launch_cost_grad(bool grad, const OtArgs& a, const OtPlan& p, cudaStream_t st) {
+  dim3 grid(a.B, p.nsplit);
+  if (!grad) {
+    auto kern = ot_cost_kernel<DT, MP, NW, TPW>;
+    CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_cost));
+    kern<<<grid, NW * 32, p.smem_cost, st>>>(a);
+  } else {
+    auto kern = ot_grad_kernel<DT, MP, NW, TPW>;
+    CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_grad));
+    kern<<<grid, NW * 32, p.smem_grad, st>>>(a);
+  }
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}
+
+template <int DT, int MP>
+int dispatch_cfg(bool grad, const OtArgs& a, const OtPlan& p, cudaStream_t st) {
+  if (p.nwarps == 4) return launch_cost_grad<DT, MP, 4, 1>(grad, a, p, st);
+  return launch_cost_grad<DT, MP, 8, (MP == 64 ? 2 : 3)>(grad, a, p, st);
+}
+
+template <int DT>
+int dispatch_mp(bool grad, const OtArgs& a, const OtPlan& p, cudaStream_t st) {
+  switch (p.MP) {
+    case 16: return dispatch_cfg<DT, 16>(grad, a, p, st);
+    case 32: return dispatch_cfg<DT, 32>(grad, a, p, st);
+    default: return dispatch_cfg<DT, 64>(grad, a, p, st);
+  }
+}
+
+template <int MP>
+int launch_ipot_mp(const IpotArgs& a, int rpt, cudaStream_t st, bool* handled) {
+  *handled = true;
+#define CE_IPOT_CASE(R) \
+  if (rpt <= R) { ot_ipot_kernel<MP, R><<<a.B, 256, 0, st>>>(a); return CE_OK; }
+  CE_IPOT_CASE(1) CE_IPOT_CASE(2) CE_IPOT_CASE(4) CE_IPOT_CASE(7) CE_IPOT_CASE(9)
+  CE_IPOT_CASE(13) CE_IPOT_CASE(19)
+#undef CE_IPOT_CASE
+  *handled = false;
+  return CE_OK;
+}
+
+}  // namespace
+}  // namespace ce
+
+using namespace ce;
+
+extern "C" size_t ce_ot_workspace_bytes(int B, int M, int N, int D) {
+  OtPlan p;
+  if (make_plan(M, N, &p) != CE_OK) return 0;
+  int Nld = (N + 3) / 4 * 4;
+  size_t bytes = 0;
+  bytes += align_up(sizeof(float) * (size_t)B * N * p.MP, 256);       // S / W
+  bytes += align_up(sizeof(float) * (size_t)B * p.MP, 256);           // nx2 / ax
+  bytes += align_up(sizeof(float) * (size_t)B * Nld, 256);            // ny2 / ay
+  bytes += align_up(sizeof(float) * (size_t)B * 2 * N * p.MP, 256);   // big-shape solver scratch
+  if (p.nsplit > 1) bytes += align_up(sizeof(float) * (size_t)B * M * D, 256);  // dx accumulators
+  return bytes + 1024;
+}
+
+extern "C" int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* img,
+                             int64_t img_bstride, const void* txt_mask, int64_t txt_mstride,
+                             const void* img_mask, int64_t img_mstride, int mask_kind, int B, int M,
+                             int N, int D, int dtype, float beta, int iters, int k,
+                             float loss_scale, float* dist, float* loss, void* dtxt, void* dimg,
+                             void* dimg_slot0, void* workspace, size_t workspace_bytes,
+                             ce_stream_t stream) {
+  CE_TRY(check_device());
+  if (dtype != CE_F32 && dtype != CE_BF16) return fail(CE_ERR_DTYPE, "OT: unknown dtype %d", dtype);
+  if (mask_kind != CE_MASK_NUM_I64 && mask_kind != CE_MASK_PAD_U8)
+    return fail(CE_ERR_ARG, "OT: unknown mask_kind %d", mask_kind);
+  if (B < 0 || D < 8 || D % 8 != 0) return fail(CE_ERR_SHAPE, "OT: need B >= 0 and D a multiple of 8 (B=%d D=%d)", B, D);
+  if (iters < 0 || k < 1) return fail(CE_ERR_ARG, "OT: need iters >= 0 and k >= 1");
+  if (!(beta > 0.f)) return fail(CE_ERR_ARG, "OT: beta must be positive");
+  if ((dtxt == nullptr) != (dimg == nullptr)) return fail(CE_ERR_ARG, "OT: pass both gradient buffers or neither");
+  const size_t esz = dtype == CE_F32 ? 4 : 2;
+  if (((uintptr_t)txt | (uintptr_t)img | (uintptr_t)dtxt | (uintptr_t)dimg) & 15)
+    return fail(CE_ERR_ALIGN, "OT: embedding pointers must be 16-byte aligned");
+  if ((txt_bstride * esz) % 16 || (img_bstride * esz) % 16)
+    return fail(CE_ERR_ALIGN, "OT: sample strides must keep 16-byte alignment");
+  OtPlan p;
+  CE_TRY(make_plan(M, N, &p));
+  if (workspace_bytes < ce_ot_workspace_bytes(B, M, N, D))
+    return fail(CE_ERR_WORKSPACE, "OT: workspace too small (%zu < %zu)", workspace_bytes, ce_ot_workspace_bytes(B, M, N, D));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (B == 0) {
+    if (loss) CE_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    return CE_OK;
+  }
+  const int Nld = (N + 3) / 4 * 4;
+  Carver cv(workspace);
+  OtArgs a{};
+  a.txt = txt; a.img = img; a.txt_bs = txt_bstride; a.img_bs = img_bstride;
+  a.B = B; a.M = M; a.N = N; a.D = D; a.tiles_per_cta = p.tiles_per_cta;
+  a.S = cv.take<float>((size_t)B * N * p.MP);
+  a.nx2 = cv.take<float>((size_t)B * p.MP);
+  a.ny2 = cv.take<float>((size_t)B * Nld);
+  float* scratch = cv.take<float>((size_t)B * 2 * N * p.MP);
+  a.Nld = Nld; a.dtxt = dtxt; a.dimg = dimg; a.nsplit = p.nsplit;
+  a.dx_acc = p.nsplit > 1 ? cv.take<float>((size_t)B * M * D) : nullptr;
+
+  if (dtype == CE_F32) CE_TRY(dispatch_mp<CE_F32>(false, a, p, st));
+  else CE_TRY(dispatch_mp<CE_BF16>(false, a, p, st));
+
+  IpotArgs ia{};
+  ia.S = a.S; ia.nx2 = a.nx2; ia.ny2 = a.ny2; ia.txt_mask = txt_mask; ia.img_mask = img_mask;
+  ia.txt_ms = txt_mstride; ia.img_ms = img_mstride; ia.mask_kind = mask_kind;
+  ia.B = B; ia.M = M; ia.N = N; ia.Nld = Nld; ia.beta = beta; ia.eps = 1e-5f; ia.scale = loss_scale;
+  ia.iters = iters; ia.k = k; ia.dist = dist;
+  bool handled = false;
+  switch (p.MP) {
+    case 16: CE_TRY(launch_ipot_mp<16>(ia, p.rpt, st, &handled)); break;
+    case 32: CE_TRY(launch_ipot_mp<32>(ia, p.rpt, st, &handled)); break;
+    default: CE_TRY(launch_ipot_mp<64>(ia, p.rpt, st, &handled)); break;
+  }
+  if (!handled) {
+    IpotBigArgs ba{ia, scratch, p.MP};
+    size_t sm = sizeof(float) * (4 * (size_t)p.MP + 3 * (size_t)N);
+    ot_ipot_big_kernel<<<B, 256, sm, st>>>(ba);
+  }
+  CE_LAUNCH_CHECK();
+
+  if (dtxt != nullptr) {
+    if (p.nsplit > 1) CE_CUDA_TRY(cudaMemsetAsync(a.dx_acc, 0, sizeof(float) * (size_t)B * M * D, st));
+    if (dtype == CE_F32) CE_TRY(dispatch_mp<CE_F32>(true, a, p, st));
+    else CE_TRY(dispatch_mp<CE_BF16>(true, a, p, st));
+    if (p.nsplit > 1) {
+      int blocks = (int)std::min<int64_t>(((int64_t)B * M * D + 255) / 256, 148 * 8);
+      if (dtype == CE_F32) ot_dx_finish_kernel<CE_F32><<<blocks, 256, 0, st>>>(a, p.MP);
+      else ot_dx_finish_kernel<CE_BF16><<<blocks, 256, 0, st>>>(a, p.MP);
+      CE_LAUNCH_CHECK();
+    }
+  }
+  {
+    void* slot = dtxt != nullptr ? dimg_slot0 : nullptr;
+    int blocks = slot ? (int)std::min<int64_t>(((int64_t)B * D + 255) / 256, 148 * 4) : 1;
+    if (dtype == CE_F32) ot_tail_kernel<CE_F32><<<blocks, 256, 0, st>>>(dist, B, loss_scale, loss, slot, img_bstride, D);
+    else ot_tail_kernel<CE_BF16><<<blocks, 256, 0, st>>>(dist, B, loss_scale, loss, slot, img_bstride, D);
+    CE_LAUNCH_CHECK();
+  }
+  return CE_OK;
+}
+
+extern "C" int ce_ot_cost_matrix(const void* x, const void* y, int B, int M, int N, int D,
+                                 int dtype, float eps, float* cost, ce_stream_t stream) {
+  CE_TRY(check_device());
+  if (dtype != CE_F32 && dtype != CE_BF16) return fail(CE_ERR_DTYPE, "cost_matrix: unknown dtype %d", dtype);
+  if (B < 0 || M < 0 || N < 0 || D < 1) return fail(CE_ERR_SHAPE, "cost_matrix: bad shape");
+  int64_t warps = (int64_t)B * M * N;
+  if (warps == 0) return CE_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int64_t blocks = (warps * 32 + 255) / 256;
+  if (blocks > 0x7fffffff) return fail(CE_ERR_SHAPE, "cost_matrix: too large");
+  if (dtype == CE_F32) ot_cost_matrix_kernel<CE_F32><<<(int)blocks, 256, 0, st>>>(x, y, B, M, N, D, eps, cost);
+  else ot_cost_matrix_kernel<CE_BF16><<<(int)blocks, 256, 0, st>>>(x, y, B, M, N, D, eps, cost);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}
+
+extern "C" int ce_ot_ipot(const float* cost, const uint8_t* x_pad, const uint8_t* y_pad, int B, int M,
+                          int N, float beta, int iters, int k, float* plan, ce_stream_t stream) {
+  CE_TRY(check_device());
+  if (B < 0 || M < 1 || N < 1) return fail(CE_ERR_SHAPE, "ipot: bad shape");
+  if (iters < 0 || k < 1 || !(beta > 0.f)) return fail(CE_ERR_ARG, "ipot: need iters >= 0, k >= 1, beta > 0");
+  if (B == 0) return CE_OK;
+  size_t sm = sizeof(float) * 2 * ((size_t)M + N);
+  if (sm > 200 * 1024) return fail(CE_ERR_SHAPE, "ipot: M+N too large");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CE_CUDA_TRY(cudaFuncSetAttribute(ot_ipot_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  ot_ipot_plain_kernel<<<B, 256, sm, st>>>(cost, x_pad, y_pad, B, M, N, beta, iters, k, plan);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}
+
+extern "C" int ce_ot_trace(const float* x, int B, int n, float* out, ce_stream_t stream) {
+  CE_TRY(check_device());
+  if (B < 0 || n < 0) return fail(CE_ERR_SHAPE, "trace: bad shape");
+  if (B == 0) return CE_OK;
+  ot_trace_kernel<<<(B + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, B, n, out);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}
+
+extern "C" int ce_scale_inplace(void* x, int64_t rows, int64_t row_len, int64_t row_stride,
+                                int dtype, const float* g, ce_stream_t stream) {
+  CE_TRY(check_device());
+  if (dtype != CE_F32 && dtype != CE_BF16) return fail(CE_ERR_DTYPE, "scale: unknown dtype %d", dtype);
+  int64_t total = rows * row_len;
+  if (total <= 0) return CE_OK;
+  int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == CE_F32) scale_inplace_kernel<CE_F32><<<blocks, 256, 0, st>>>(x, rows, row_len, row_stride, g);
+  else scale_inplace_kernel<CE_BF16><<<blocks, 256, 0, st>>>(x, rows, row_len, row_stride, g);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}

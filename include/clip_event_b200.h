@@ -1,0 +1,191 @@
+/* clip_event_b200.h -- C ABI of the B200-native CLIP-Event training loss head.
+ *
+ * Drop-in boundary for ONE hot path of limanling/clip-event:
+ *   similarity scoring   src/clip-event/model_clip.py:495-528   (CLIP.forward tail)
+ *   InfoNCE criterion    src/clip-event/model_clip.py:620-662   (CriterionContrastive)
+ *   OT alignment loss    src/clip-event/model_clip.py:664-715   (CriterionAlignment)
+ *   IPOT solver          src/clip-event/model_ot.py:8-84
+ * forward and backward.  The reference is pure PyTorch and has no FFI of its own, so these
+ * entry points are what a ctypes/cffi stub inside the reference's model_clip.py / model_ot.py
+ * would bind (INTEGRATION.md shows that stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory,
+ *     including workspaces (sizes from the *_workspace_bytes queries); the library never allocates
+ *     device memory and keeps no state besides a thread-local error string;
+ *   - tensors are row-major and contiguous unless a stride argument says otherwise; embedding
+ *     pointers must be 16-byte aligned and D a multiple of 8;
+ *   - dtype: CE_F32 = fp32 in / fp32 out, tensor-core products as 3xTF32 (fp32-level accuracy);
+ *            CE_BF16 = bf16 in / bf16 out, fp32 accumulation and fp32 softmax / solver state;
+ *   - all work is enqueued on `stream` (a cudaStream_t); no host synchronisation inside;
+ *   - return 0 on success, a negative CE_ERR_* for bad arguments, or a positive cudaError_t;
+ *     ce_last_error() describes the last failure on the calling thread.
+ *   - sm_100a only: every entry point returns CE_ERR_ARCH on another device.  No CPU fallback.
+ */
+#ifndef CLIP_EVENT_B200_H_
+#define CLIP_EVENT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ce_stream_t; /* cudaStream_t */
+
+enum {
+  CE_OK = 0,
+  CE_ERR_SHAPE = -1,
+  CE_ERR_DTYPE = -2,
+  CE_ERR_ALIGN = -3,
+  CE_ERR_WORKSPACE = -4,
+  CE_ERR_ARCH = -5,
+  CE_ERR_ARG = -6
+};
+enum { CE_F32 = 0, CE_BF16 = 1 };
+/* node-mask encodings accepted by the OT entry points */
+enum { CE_MASK_NUM_I64 = 0 /* reference `*_num`: int64, valid = nonzero  (model_clip.py:688-690) */,
+       CE_MASK_PAD_U8 = 1  /* reference `*_pad`: bool/uint8, pad = nonzero (model_ot.py:66-74)   */ };
+
+int ce_version(void);
+const char* ce_last_error(void);
+/* 0 if the current CUDA device is sm_100 (B200), CE_ERR_ARCH otherwise. */
+int ce_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Similarity scoring + InfoNCE, over-batch mode  (model_clip.py:496-508 + 633-662, 'ce')
+ *
+ * Rows are images, columns are descriptions.  One fused tcgen05 GEMM L = s * I^ T^t is never
+ * materialised: its epilogue produces the row log-sum-exp (image side) and, through the identity
+ * logits_per_text[index_pos] == L[:, index_pos]^t, the column log-sum-exp of the positive columns
+ * (text side).
+ *
+ * The entry points are written for a column-sharded multi-GPU run: `img` holds ALL
+ * R (gathered) images, `txt` the C LOCAL descriptions whose global column index starts at
+ * `col_offset`.  Single GPU: R = B, C = B*T, col_offset = 0, world = 1.
+ *
+ *   img          [R, D]   image_features (un-normalised)
+ *   txt          [C, D]   text_features  (un-normalised), local columns
+ *   logit_scale  [1]      fp32, the log of the temperature inverse (model_clip.py:330,502)
+ *   labels_i     [R]      int64 GLOBAL column index of each image's positive  (labels_per_image)
+ *   labels_t     [C]      int64 GLOBAL row index each local description belongs to (labels_per_text)
+ *   index_pos    [P]      int64 LOCAL column indices used for the text-side loss  (index_pos)
+ * ------------------------------------------------------------------------------------------ */
+size_t ce_contrastive_workspace_bytes(int R, int C, int P, int D, int dtype);
+
+/* Phase 1: GEMM + local statistics.
+ *   row_part  [R, 4] fp32 out: per image (max2, sum2, positive logit, 0): running max and sum of
+ *             the base-2 scaled logits over the LOCAL columns, and L[r, labels_i[r]] if that column
+ *             is local (else 0).  All-gather these blocks across ranks.
+ *   sums      [4]    fp32 out: {sum_p (colLSE_p - L[labels_t[pos_p], pos_p]), P, 0, 0}
+ * Stashes norms / column LSE / split operands in `workspace` for the backward. */
+int ce_contrastive_fwd_partial(const void* img, const void* txt, const float* logit_scale,
+                               const int64_t* labels_i, const int64_t* labels_t,
+                               const int64_t* index_pos, int R, int C, int P, int D,
+                               int64_t col_offset, int dtype, float* row_part, float* sums,
+                               void* workspace, size_t workspace_bytes, ce_stream_t stream);
+
+/* Phase 2: merge `world` row_part blocks ([world, R, 4], this rank's own included), reduce the
+ * `world` sums blocks ([world, 4]) and emit the losses.  loss_i = mean_r(rowLSE - L[r,label]),
+ * loss_t = mean_p(...) over the GLOBAL P.  Writes the global row LSE into the workspace (same
+ * R, C, P, D, dtype as phase 1) for the backward. */
+int ce_contrastive_fwd_finish(const float* row_part_all, const float* sums_all, int world, int R,
+                              int C, int P, int D, int dtype, float* loss_i, float* loss_t,
+                              void* workspace, size_t workspace_bytes, ce_stream_t stream);
+
+/* Backward phase 1.  g_i / g_t are device scalars dL/dloss_i, dL/dloss_t; R_total / P_total the
+ * global means' denominators.  Produces
+ *   dtxt          [C, D] in `dtype` -- complete (normalisation backward applied)
+ *   dimg_hat_part [R, D] fp32       -- s * G T^ for the LOCAL columns, BEFORE the normalisation
+ *                                      backward; sum over ranks (reduce-scatter), then call
+ *                                      ce_contrastive_bwd_finish on the local rows
+ *   dlogit_scale_part [1] fp32      -- sum over ranks. */
+int ce_contrastive_bwd_partial(const void* img, const void* txt, const float* logit_scale,
+                               const int64_t* labels_i, const int64_t* labels_t,
+                               const int64_t* index_pos, int R, int C, int P, int D,
+                               int64_t col_offset, int dtype, const float* g_i, const float* g_t,
+                               int R_total, int P_total, void* dtxt, float* dimg_hat_part,
+                               float* dlogit_scale_part, void* workspace, size_t workspace_bytes,
+                               ce_stream_t stream);
+
+/* Backward phase 2: dimg = (d - i^ (i^ . d)) / |i| on `rows` rows (model_clip.py:496 backward). */
+int ce_contrastive_bwd_finish(const void* img_rows, const float* dimg_hat_rows, int rows, int D,
+                              int dtype, void* dimg_rows, ce_stream_t stream);
+
+/* Single-GPU convenience wrappers (world = 1): forward then backward with the same workspace. */
+int ce_contrastive_fwd(const void* img, const void* txt, const float* logit_scale,
+                       const int64_t* labels_i, const int64_t* labels_t, const int64_t* index_pos,
+                       int B, int BT, int P, int D, int dtype, float* loss_i, float* loss_t,
+                       void* workspace, size_t workspace_bytes, ce_stream_t stream);
+int ce_contrastive_bwd(const void* img, const void* txt, const float* logit_scale,
+                       const int64_t* labels_i, const int64_t* labels_t, const int64_t* index_pos,
+                       int B, int BT, int P, int D, int dtype, const float* g_i, const float* g_t,
+                       void* dimg, void* dtxt, float* dlogit_scale, void* workspace,
+                       size_t workspace_bytes, ce_stream_t stream);
+
+/* Materialised logits for consumers that need the matrix itself
+ * (src/preprocess/preprocess_description_contrastive.py:127-134):
+ *   out[r, c] = exp(logit_scale) * <a_r, b_c> / (|a_r| |b_c|),  out is [Ra, Rb] fp32.
+ * CLIP.forward returns (logits_per_image = f(img, txt), logits_per_text = f(txt, img)). */
+int ce_similarity_logits(const void* a, const void* b, const float* logit_scale, int Ra, int Rb,
+                         int D, int dtype, float* out, void* workspace, size_t workspace_bytes,
+                         ce_stream_t stream);
+size_t ce_similarity_workspace_bytes(int Ra, int Rb, int D, int dtype);
+
+/* ------------------------------------------------------------------------------------------
+ * OT graph alignment  (model_clip.py:679-715 + model_ot.py:8-84)
+ *
+ *   txt   [B, M, D]  text node embeddings, sample stride txt_bstride elements
+ *   img   [B, N, D]  image node embeddings AFTER the whole-image slot: pass object_vec + D with
+ *                    img_bstride = (N+1)*D to drop slot 0 without a copy (model_clip.py:686)
+ *   masks per `mask_kind`; *_mstride is the per-sample stride of the mask arrays in elements
+ *   beta / iters / k   IPOT parameters (model_ot.py:68: 0.5 / 50 / 1)
+ *
+ * ce_ot_fwd_bwd computes in ONE pass over the embeddings
+ *   dist   [B] fp32      model_ot.py:83
+ *   loss   [1] fp32      loss_scale * sum_b dist[b]         (model_clip.py:707: loss_scale = 0.01)
+ *   dtxt / dimg          loss_scale * d(sum_b dist[b]) / d(txt, img), same layout/strides/dtype as
+ *                        the inputs (pass NULL for both to skip the backward); IPOT is not
+ *                        differentiated through (model_ot.py:32,81,83); padded entries get 0.
+ *   dimg_slot0           if non-NULL, [B] rows of D elements with stride img_bstride that are
+ *                        zero-filled (the dropped slot's gradient).
+ * Scale the returned gradients by dL/dloss with ce_scale_inplace (a no-op launch when it is 1).
+ * ------------------------------------------------------------------------------------------ */
+size_t ce_ot_workspace_bytes(int B, int M, int N, int D);
+int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* img, int64_t img_bstride,
+                  const void* txt_mask, int64_t txt_mstride, const void* img_mask,
+                  int64_t img_mstride, int mask_kind, int B, int M, int N, int D, int dtype,
+                  float beta, int iters, int k, float loss_scale, float* dist, float* loss,
+                  void* dtxt, void* dimg, void* dimg_slot0, void* workspace,
+                  size_t workspace_bytes, ce_stream_t stream);
+
+/* The solver's building blocks with the reference's own granularity (model_ot.py), fp32:
+ *   ce_ot_cost_matrix : cost_matrix_cosine  [B,M,D],[B,N,D] -> 1 - cos [B,M,N]  (model_ot.py:8-18)
+ *   ce_ot_ipot        : ipot                C [B,M,N] -> T [B,N,M]              (model_ot.py:32-63)
+ *   ce_ot_trace       : trace               [B,n,n] -> [B]                      (model_ot.py:21-29)
+ */
+int ce_ot_cost_matrix(const void* x, const void* y, int B, int M, int N, int D, int dtype,
+                      float eps, float* cost, ce_stream_t stream);
+int ce_ot_ipot(const float* cost, const uint8_t* x_pad, const uint8_t* y_pad, int B, int M, int N,
+               float beta, int iters, int k, float* plan, ce_stream_t stream);
+int ce_ot_trace(const float* x, int B, int n, float* out, ce_stream_t stream);
+
+/* x[i] *= *g for i < n (n elements of `dtype`, rows of `row_len` elements `row_stride` apart);
+ * returns immediately on the device when *g == 1. */
+int ce_scale_inplace(void* x, int64_t rows, int64_t row_len, int64_t row_stride, int dtype,
+                     const float* g, ce_stream_t stream);
+
+/* Debug / self-test: C[M,N] (fp32) = A * B^t through the same tcgen05 + TMA main loop the
+ * similarity GEMM uses.  a_mn_major / b_mn_major select the operand layouts:
+ *   K-major : A is [M, K] row-major, B is [N, K] row-major
+ *   MN-major: A is [K, M] row-major, B is [K, N] row-major
+ * CE_F32 runs the three-product tf32 path with (hi, lo) = (A, A), i.e. returns 3 * A * B^t for
+ * tf32-representable inputs. */
+int ce_debug_gemm(const void* A, const void* B, float* C, int M, int N, int K, int dtype,
+                  int a_mn_major, int b_mn_major, int split_k, ce_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIP_EVENT_B200_H_ */
