@@ -65,7 +65,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap(CUtensorMap* out, const void* ptr, bool fp32, uint64_t inner, uint64_t outer,
-              uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer) {
+              uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer, bool atom32) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(CE_ERR_ARCH, "cuTensorMapEncodeTiled is not available from this driver");
   const uint64_t esz = fp32 ? 4 : 2;
@@ -77,7 +77,8 @@ int make_tmap(CUtensorMap* out, const void* ptr, bool fp32, uint64_t inner, uint
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(CE_ERR_ARG, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r,

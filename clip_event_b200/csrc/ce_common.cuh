@@ -267,14 +267,15 @@ __device__ __forceinline__ void tmem_ld_wait() {
 //   K-major operand : rows of 128 B (one swizzle atom along K), 8-row groups `sbo` bytes apart.
 //   MN-major operand: 128 B of MN per row, rows are K; 8-K-row groups `sbo` bytes apart,
 //                     128-B MN chunks `lbo` bytes apart.
+//   32-bit MN-major operands need the SWIZZLE_128B_BASE32B layout (type 1): 4-K-row groups.
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
+                                                   uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fffu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version for Blackwell
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= (uint64_t)1 << 46;            // descriptor version for Blackwell
+  d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 // Instruction descriptor for kind::f16 (bf16 in) / kind::tf32, fp32 accumulate.

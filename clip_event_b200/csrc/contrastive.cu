@@ -34,9 +34,13 @@ struct EpiStats {
     const float* logit_scale;
     float2* part;  // [M, num_n_blk]  (max2, sum2) of the base-2 scaled logits
     int M, N, num_n_blk;
+    const int* lab;     // [M] column of the row's positive (or -1)
+    float* lab_logit;   // [M] natural-log logit at that column, taken from the SAME accumulator so
+                        //     that the tensor-core rounding cancels in (LSE - positive logit)
   };
   Params p;
   float rs, m2, l;
+  int lab;
   __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et) {
     for (int c = et; c < BN; c += 128) {
       int col = n_blk * BN + c;
@@ -47,15 +51,22 @@ struct EpiStats {
     rs = ok ? expf(__ldg(p.logit_scale)) * kLog2e * __ldg(p.rinv_row + row) : 0.f;
     m2 = -INFINITY;
     l = 0.f;
+    lab = ok ? __ldg(p.lab + row) : -1;
   }
   __device__ __forceinline__ void chunk(const float* acc, int col0, int lcol0, const float* s_epi,
-                                        int, bool) {
+                                        int row, bool) {
     float v[32];
     float cm = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       v[i] = (col0 + i < p.N) ? acc[i] * rs * s_epi[lcol0 + i] : -INFINITY;
       cm = fmaxf(cm, v[i]);
+    }
+    if ((unsigned)(lab - col0) < 32u) {
+      float pick = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pick = (col0 + i == lab) ? v[i] : pick;
+      p.lab_logit[row] = pick * kLn2;
     }
     if (cm == -INFINITY) return;
     float mn = fmaxf(m2, cm);
@@ -288,6 +299,23 @@ __device__ __forceinline__ void warp_merge_ml(float& m, float& l) {
   m = M;
 }
 
+// Resolve the positives' columns for both GEMMs and clear their logit slots.
+__global__ void label_prep_kernel(const int64_t* labels_i, const int64_t* labels_t,
+                                  const int64_t* index_pos, int R, int C, int P, int64_t col_offset,
+                                  int* lab_local, float* lab_logit_i, int* lab_t, float* lab_logit_t) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) {
+    int64_t lab = labels_i[i] - col_offset;
+    lab_local[i] = (lab >= 0 && lab < C) ? (int)lab : -1;
+    lab_logit_i[i] = 0.f;
+  } else if (i < R + P) {
+    int p = i - R;
+    int64_t row = labels_t[index_pos[p]];
+    lab_t[p] = (row >= 0 && row < R) ? (int)row : -1;
+    lab_logit_t[p] = 0.f;
+  }
+}
+
 struct ItemArgs {
   const void* img; const void* txt;
   const float* logit_scale;
@@ -298,7 +326,8 @@ struct ItemArgs {
   int R, C, P, D;
   int64_t col_offset;
   float4* row_part;   // [R]  (max2, sum2, label logit if the label column is local, 0)
-  int* lab_local;     // [R]
+  const float* lab_logit_i;  // [R]
+  const float* lab_logit_t;  // [P]
   float* lse2_col;    // [P]
   float* item_t;      // [P]  colLSE - positive logit
 };
@@ -308,7 +337,6 @@ template <int DT>
 __global__ void fwd_items_kernel(ItemArgs a) {
   int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
-  const float s = expf(__ldg(a.logit_scale));
   if (it < a.R) {
     int r = it;
     float m = -INFINITY, l = 0.f;
@@ -318,14 +346,7 @@ __global__ void fwd_items_kernel(ItemArgs a) {
       if (mn != -INFINITY) { l = l * ex2(m - mn) + pr.y * ex2(pr.x - mn); m = mn; }
     }
     warp_merge_ml(m, l);
-    int64_t lab = a.labels_i[r] - a.col_offset;
-    bool local = lab >= 0 && lab < a.C;
-    float logit = 0.f;
-    if (local) logit = s * a.rinv_i[r] * a.rinv_t[lab] * warp_dot<DT>(a.img, r, a.txt, lab, a.D);
-    if (lane == 0) {
-      a.row_part[r] = make_float4(m, l, logit, 0.f);
-      a.lab_local[r] = local ? (int)lab : -1;
-    }
+    if (lane == 0) a.row_part[r] = make_float4(m, l, a.lab_logit_i[r], 0.f);
   } else if (it < a.R + a.P) {
     int p = it - a.R;
     float m = -INFINITY, l = 0.f;
@@ -336,12 +357,9 @@ __global__ void fwd_items_kernel(ItemArgs a) {
     }
     warp_merge_ml(m, l);
     float lse2 = m + log2f(l);
-    int64_t col = a.index_pos[p];
-    int64_t row = a.labels_t[col];
-    float logit = s * a.rinv_i[row] * a.rinv_t[col] * warp_dot<DT>(a.img, row, a.txt, col, a.D);
     if (lane == 0) {
       a.lse2_col[p] = lse2;
-      a.item_t[p] = lse2 * kLn2 - logit;
+      a.item_t[p] = lse2 * kLn2 - a.lab_logit_t[p];
     }
   }
 }
@@ -460,7 +478,8 @@ __global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, 
 struct CtrWs {
   float *rinv_i, *norm_i, *rinv_t, *norm_t, *rinv_p;
   float *lse2_row, *lse2_col, *item_t, *col_lse2;
-  int *lab_local, *col_lab;
+  int *lab_local, *col_lab, *lab_t;
+  float *lab_logit_i, *lab_logit_t;
   float2 *part_i, *part_t;
   float4* row_part;
   float *sums, *dls_part;
@@ -487,7 +506,8 @@ CtrWs carve(void* base, int R, int C, int P, int D, int dtype) {
   w.rinv_p = cv.take<float>(P);
   w.lse2_row = cv.take<float>(R); w.lse2_col = cv.take<float>(P); w.item_t = cv.take<float>(P);
   w.col_lse2 = cv.take<float>(C);
-  w.lab_local = cv.take<int>(R); w.col_lab = cv.take<int>(C);
+  w.lab_local = cv.take<int>(R); w.col_lab = cv.take<int>(C); w.lab_t = cv.take<int>(P);
+  w.lab_logit_i = cv.take<float>(R); w.lab_logit_t = cv.take<float>(P);
   w.part_i = cv.take<float2>((size_t)R * w.nblk_i);
   w.part_t = cv.take<float2>((size_t)P * w.nblk_t);
   w.row_part = cv.take<float4>(R);
@@ -548,20 +568,23 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const in
   CE_TRY(run_prep<DT>(img, nullptr, R, D, w.rinv_i, w.norm_i, TF ? w.img_p[0] : nullptr, w.img_p[1], st));
   CE_TRY(run_prep<DT>(txt, nullptr, C, D, w.rinv_t, w.norm_t, TF ? w.txt_p[0] : nullptr, w.txt_p[1], st));
   CE_TRY(run_prep<DT>(txt, index_pos, P, D, w.rinv_p, nullptr, w.pos_p[0], w.pos_p[1], st));
+  label_prep_kernel<<<(R + P + 255) / 256, 256, 0, st>>>(labels_i, labels_t, index_pos, R, C, P, col_offset,
+                                                         w.lab_local, w.lab_logit_i, w.lab_t, w.lab_logit_t);
+  CE_LAUNCH_CHECK();
   GemmOperand oi = operand<DT>(img, w.img_p, R, D, 0);
   GemmOperand ot = operand<DT>(txt, w.txt_p, C, D, 0);
   GemmOperand op = operand<DT>(w.pos_p[0], w.pos_p, P, D, 0);
   {
-    typename EpiStats<BN>::Params ep{w.rinv_i, w.rinv_t, ls, w.part_i, R, C, w.nblk_i};
+    typename EpiStats<BN>::Params ep{w.rinv_i, w.rinv_t, ls, w.part_i, R, C, w.nblk_i, w.lab_local, w.lab_logit_i};
     CE_TRY((launch_gemm<TF, BN, EpiStats<BN>>(oi, ot, D, 1, ep, st)));
   }
   {
-    typename EpiStats<BN>::Params ep{w.rinv_p, w.rinv_i, ls, w.part_t, P, R, w.nblk_t};
+    typename EpiStats<BN>::Params ep{w.rinv_p, w.rinv_i, ls, w.part_t, P, R, w.nblk_t, w.lab_t, w.lab_logit_t};
     CE_TRY((launch_gemm<TF, BN, EpiStats<BN>>(op, oi, D, 1, ep, st)));
   }
   ItemArgs ia{img, txt, ls, labels_i, labels_t, index_pos, w.rinv_i, w.rinv_t, w.part_i, w.nblk_i,
               w.part_t, w.nblk_t, R, C, P, D, col_offset, reinterpret_cast<float4*>(row_part),
-              w.lab_local, w.lse2_col, w.item_t};
+              w.lab_logit_i, w.lab_logit_t, w.lse2_col, w.item_t};
   int blocks = ((R + P) * 32 + 255) / 256;
   fwd_items_kernel<DT><<<blocks, 256, 0, st>>>(ia);
   CE_LAUNCH_CHECK();

@@ -10,6 +10,8 @@
 // (d x^ = -dC y^,  dx = (dx^ - x^ (x^.dx^)) / |x|,  x^.dx^ = -sum_n dC[m,n] S^[m,n]).
 // The contractions run on the tensor cores through warp-level mma (tf32, 3-way split in fp32
 // mode so the cost matrix keeps fp32 accuracy: IPOT amplifies cost error by iters/beta).
+#include <algorithm>
+
 #include "ce_common.cuh"
 
 namespace ce {
@@ -117,6 +119,48 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
     stage_rows<DT, kLdA>(xs, xg, MP, a.M, a.D, d0, NT);
     stage_rows<DT, kLdA>(ys, yg, rows, rows_valid, a.D, d0, NT);
     __syncthreads();
+    if constexpr (NSPLIT == 3) {
+      // fp32 mode.  The tensor core truncates its fp32 accumulator after every instruction, a bias
+      // that grows with the accumulator's magnitude and the chain length (measured: ~4e-6
+      // relative over D = 512) and that IPOT then amplifies by iters/beta.  So each 32-column
+      // step is accumulated from zero (12 instructions, small partial sums) and folded into the
+      // running sum with an ordinary round-to-nearest add.
+#pragma unroll
+      for (int i = 0; i < TPW; ++i) {
+        int tile = w + i * NWARPS;
+        if (tile < my_tiles) {
+          float tacc[NJ][4];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tacc[j][c] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < kDC / 8; ++ks) {
+            const float* yr = ys + (tile * 16 + g) * kLdA + ks * 8 + t;
+            float av[4] = {yr[0], yr[8 * kLdA], yr[4], yr[8 * kLdA + 4]};
+            yss[i][0] += av[0] * av[0] + av[2] * av[2];
+            yss[i][1] += av[1] * av[1] + av[3] * av[3];
+            uint32_t ahi[4], alo[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) split_tf32<NSPLIT>(av[c], ahi[c], alo[c]);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+              float b0 = xs[(8 * j + g) * kLdA + ks * 8 + t];
+              float b1 = xs[(8 * j + g) * kLdA + ks * 8 + t + 4];
+              if (i == 0) xss[j] += b0 * b0 + b1 * b1;
+              uint32_t bhi[2], blo[2];
+              split_tf32<NSPLIT>(b0, bhi[0], blo[0]);
+              split_tf32<NSPLIT>(b1, bhi[1], blo[1]);
+              mma_split<NSPLIT>(tacc[j], ahi, alo, bhi, blo);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][j][c] += tacc[j][c];
+        }
+      }
+    } else {
 #pragma unroll
     for (int ks = 0; ks < kDC / 8; ++ks) {
       uint32_t bhi[NJ][2], blo[NJ][2];
@@ -143,6 +187,7 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
           for (int j = 0; j < NJ; ++j) mma_split<NSPLIT>(acc[i][j], ahi, alo, bhi[j], blo[j]);
         }
       }
+    }
     }
     __syncthreads();
   }
@@ -682,10 +727,11 @@ template <int DT>
 __global__ void ot_tail_kernel(const float* dist, int B, float scale, float* loss, void* slot0,
                                int64_t bs, int D) {
   using T = typename In<DT>::type;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && loss != nullptr) {
+  if (blockIdx.x == 0 && threadIdx.x < 32 && loss != nullptr) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dist[b];
-    *loss = s * scale;
+    for (int b = threadIdx.x; b < B; b += 32) s += dist[b];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *loss = s * scale;
   }
   if (slot0 != nullptr) {
     int64_t total = (int64_t)B * D;

@@ -143,6 +143,10 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     const uint32_t a_lbo = gs.a_mn ? Cfg::kBK * kSwizzleBytes : 16, b_lbo = gs.b_mn ? Cfg::kBK * kSwizzleBytes : 16;
     const uint32_t a_kstep = gs.a_mn ? Cfg::kUmmaK * kSwizzleBytes : 32;
     const uint32_t b_kstep = gs.b_mn ? Cfg::kUmmaK * kSwizzleBytes : 32;
+    // tf32 MN-major operands only exist in the 32-byte-atom flavour of the 128-byte swizzle
+    // (4-row K groups, 512 B apart); everything else uses the plain 128-byte swizzle.
+    const uint32_t a_lt = (TF32X3 && gs.a_mn) ? 1u : 2u, b_lt = (TF32X3 && gs.b_mn) ? 1u : 2u;
+    const uint32_t a_sbo = (TF32X3 && gs.a_mn) ? 512u : 1024u, b_sbo = (TF32X3 && gs.b_mn) ? 512u : 1024u;
     int stage = 0; uint32_t phase = 0;
     int acc_stage = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -161,11 +165,11 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
 #pragma unroll
         for (int kk = 0; kk < Cfg::kBK / Cfg::kUmmaK; ++kk) {
           const uint32_t first = (kb == kb0 && kk == 0) ? 0u : 1u;
-          const uint64_t da_hi = umma_smem_desc(sa_hi + kk * a_kstep, a_lbo, 1024);
-          const uint64_t db_hi = umma_smem_desc(sb_hi + kk * b_kstep, b_lbo, 1024);
+          const uint64_t da_hi = umma_smem_desc(sa_hi + kk * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t db_hi = umma_smem_desc(sb_hi + kk * b_kstep, b_lbo, b_sbo, b_lt);
           if constexpr (TF32X3) {
-            const uint64_t da_lo = umma_smem_desc(sa_lo + kk * a_kstep, a_lbo, 1024);
-            const uint64_t db_lo = umma_smem_desc(sb_lo + kk * b_kstep, b_lbo, 1024);
+            const uint64_t da_lo = umma_smem_desc(sa_lo + kk * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t db_lo = umma_smem_desc(sb_lo + kk * b_kstep, b_lbo, b_sbo, b_lt);
             umma<true>(tmem_d, da_lo, db_hi, idesc, first);
             umma<true>(tmem_d, da_hi, db_lo, idesc, 1u);
             umma<true>(tmem_d, da_hi, db_hi, idesc, 1u);
@@ -222,7 +226,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
 // ------------------------------------------------------------------------------------------
 // 2-D tensor map over a row-major [outer, inner] matrix with a 128-byte-wide box.
 int make_tmap(CUtensorMap* out, const void* ptr, bool fp32, uint64_t inner, uint64_t outer,
-              uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer);
+              uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer,
+              bool atom32 = false);
 
 struct GemmOperand {
   const void* ptr[2];  // hi, lo (lo null for bf16)
@@ -246,9 +251,9 @@ int build_tmaps(TmapSet* tm, GemmShape* gs, const GemmOperand& A, const GemmOper
   gs->a_mn = A.mn_major; gs->b_mn = B.mn_major;
   for (int part = 0; part < Cfg::kParts; ++part) {
     if (!A.mn_major) CE_TRY(make_tmap(&tm->a[part], A.ptr[part], TF32X3, K, A.rows, A.ld, Cfg::kBK, kBM));
-    else CE_TRY(make_tmap(&tm->a[part], A.ptr[part], TF32X3, A.rows, K, A.ld, Cfg::kBK, Cfg::kBK));
+    else CE_TRY(make_tmap(&tm->a[part], A.ptr[part], TF32X3, A.rows, K, A.ld, Cfg::kBK, Cfg::kBK, TF32X3));
     if (!B.mn_major) CE_TRY(make_tmap(&tm->b[part], B.ptr[part], TF32X3, K, B.rows, B.ld, Cfg::kBK, BN));
-    else CE_TRY(make_tmap(&tm->b[part], B.ptr[part], TF32X3, B.rows, K, B.ld, Cfg::kBK, Cfg::kBK));
+    else CE_TRY(make_tmap(&tm->b[part], B.ptr[part], TF32X3, B.rows, K, B.ld, Cfg::kBK, Cfg::kBK, TF32X3));
   }
   if (Cfg::kParts == 1) { tm->a[1] = tm->a[0]; tm->b[1] = tm->b[0]; }
   return CE_OK;

@@ -1,0 +1,188 @@
+"""Global-negative InfoNCE and sharded OT across the GPUs of one box.
+
+The reference never gathers embeddings: its ``utils.gather_tensors`` (utils.py:192-206) has no call
+site and under DDP every rank scores local negatives only (train.py:222-225).  This module is the
+"every rank scores against the global negative set" variant BASELINE.json asks for; its oracle is
+the reference loss evaluated single-process on the rank-order concatenation of all ranks' inputs.
+
+Partitioning (column shard by text, one exchange step):
+  rank r owns images [r*b, (r+1)*b) and their b*T descriptions.
+  1. all_gather(image_features)              B_g*D elements       (+ labels_per_image)
+  2. local fused GEMM  L_r = s * I^_all T^_r^t  -> per-row (max, sum, positive logit) over the local
+     columns; the text-side cross-entropy of the local positive columns is complete locally
+  3. all_gather(row statistics [B_g, 4]) + [4] text-side sums     -> loss_i, loss_t on every rank
+  4. backward: G_r local; dtxt_r = s G_r^t I^_all needs no exchange;
+     reduce_scatter(s G_r T^_r  [B_g, D] fp32) -> d I^ rows of this rank -> normalisation backward
+     all_reduce(dlogit_scale)
+OT shards by sample with no data-path exchange; only the scalar loss is all-reduced.
+
+The collectives are torch.distributed calls on the current stream (NCCL over NVLink on B200, gloo
+in the CPU tests).  ``compute`` is the per-rank kernel backend: :class:`CudaBackend` in production;
+the CPU tests inject an oracle-backed stand-in to check the choreography with world_size 2.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import functional as F_
+
+
+class CudaBackend:
+    """Per-rank compute through the C ABI phases (include/clip_event_b200.h)."""
+
+    def __init__(self):
+        self.lib = L.load()
+
+    def fwd_partial(self, img_all, txt, ls, labels_i_all, labels_t, index_pos, col_offset):
+        R, D = img_all.shape
+        C, P = txt.shape[0], index_pos.numel()
+        dt = L.dtype_code(img_all.dtype)
+        nbytes = self.lib.ce_contrastive_workspace_bytes(R, C, P, D, dt)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=img_all.device)
+        row_part = torch.empty(R, 4, dtype=torch.float32, device=img_all.device)
+        sums = torch.empty(4, dtype=torch.float32, device=img_all.device)
+        L.check(self.lib.ce_contrastive_fwd_partial(
+            img_all.data_ptr(), txt.data_ptr(), ls.data_ptr(), labels_i_all.data_ptr(), labels_t.data_ptr(),
+            index_pos.data_ptr(), R, C, P, D, int(col_offset), dt, row_part.data_ptr(), sums.data_ptr(),
+            ws.data_ptr(), nbytes, L.stream_ptr()), "contrastive fwd_partial")
+        return row_part, sums, (ws, R, C, P, D, dt)
+
+    def fwd_finish(self, row_part_all, sums_all, world, state):
+        ws, R, C, P, D, dt = state
+        out = torch.empty(2, dtype=torch.float32, device=ws.device)
+        L.check(self.lib.ce_contrastive_fwd_finish(
+            row_part_all.data_ptr(), sums_all.data_ptr(), world, R, C, P, D, dt, out.data_ptr(),
+            out.data_ptr() + 4, ws.data_ptr(), ws.numel(), L.stream_ptr()), "contrastive fwd_finish")
+        return out[0], out[1]
+
+    def bwd_partial(self, img_all, txt, ls, labels_i_all, labels_t, index_pos, col_offset, g_i, g_t,
+                    R_total, P_total, state):
+        ws, R, C, P, D, dt = state
+        dtxt = torch.empty_like(txt)
+        dimg_hat = torch.empty(R, D, dtype=torch.float32, device=txt.device)
+        dls = torch.empty(1, dtype=torch.float32, device=txt.device)
+        L.check(self.lib.ce_contrastive_bwd_partial(
+            img_all.data_ptr(), txt.data_ptr(), ls.data_ptr(), labels_i_all.data_ptr(), labels_t.data_ptr(),
+            index_pos.data_ptr(), R, C, P, D, int(col_offset), dt, g_i.data_ptr(), g_t.data_ptr(),
+            int(R_total), int(P_total), dtxt.data_ptr(), dimg_hat.data_ptr(), dls.data_ptr(),
+            ws.data_ptr(), ws.numel(), L.stream_ptr()), "contrastive bwd_partial")
+        return dtxt, dimg_hat, dls
+
+    def bwd_finish(self, img_rows, dimg_hat_rows):
+        rows, D = img_rows.shape
+        out = torch.empty_like(img_rows)
+        L.check(self.lib.ce_contrastive_bwd_finish(
+            img_rows.data_ptr(), dimg_hat_rows.data_ptr(), rows, D, L.dtype_code(img_rows.dtype),
+            out.data_ptr(), L.stream_ptr()), "contrastive bwd_finish")
+        return out
+
+
+def shard_bounds(n_global: int, world: int, rank: int):
+    """Contiguous rank-order shard [lo, hi) of n_global items (n_global must divide evenly)."""
+    if n_global % world != 0:
+        raise RuntimeError("global batch %d is not divisible by world size %d" % (n_global, world))
+    per = n_global // world
+    return rank * per, (rank + 1) * per
+
+
+def global_labels_for_rank(b_local: int, T: int, world: int, rank: int, device=None):
+    """The reference's label contract (dataset_voa.py:617-663) restated for rank-order shards:
+    labels_per_image are GLOBAL column indices, labels_per_text GLOBAL row indices, index_pos
+    LOCAL column indices."""
+    rows = torch.arange(rank * b_local, (rank + 1) * b_local, dtype=torch.int64, device=device)
+    return rows * T, rows.repeat_interleave(T), torch.arange(b_local, dtype=torch.int64, device=device) * T
+
+
+def _reduce_scatter_sum(out, inp, rank, group):
+    """reduce_scatter (NCCL); gloo has none, so the CPU tests all-reduce and slice."""
+    if dist.get_backend(group) == "gloo":
+        tmp = inp.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        out.copy_(tmp.view(-1, *out.shape)[rank])
+    else:
+        dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
+
+
+class _GlobalContrastive(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, txt, logit_scale, labels_i, labels_t, index_pos, group, compute):
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        dev = img.device
+        img_c, txt_c = img.detach().contiguous(), txt.detach().contiguous()
+        ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        labels_i = labels_i.to(device=dev, dtype=torch.int64).contiguous()
+        labels_t = labels_t.to(device=dev, dtype=torch.int64).contiguous()
+        index_pos = index_pos.to(device=dev, dtype=torch.int64).contiguous()
+        b, D = img_c.shape
+        C = txt_c.shape[0]
+        # 1. gather images and their labels (texts stay local)
+        img_all = torch.empty(world * b * D, dtype=img_c.dtype, device=dev)
+        dist.all_gather_into_tensor(img_all, img_c.view(-1), group=group)
+        img_all = img_all.view(world * b, D)
+        lab_all = torch.empty(world * b, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(lab_all, labels_i, group=group)
+        # 2. local GEMM + statistics
+        col_offset = rank * C
+        row_part, sums, state = compute.fwd_partial(img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset)
+        # 3. exchange the statistics
+        stats = torch.cat([row_part.reshape(-1), sums.reshape(-1)])
+        stats_all = torch.empty(world * stats.numel(), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(stats_all, stats, group=group)
+        stats_all = stats_all.view(world, stats.numel())
+        R = world * b
+        row_part_all = stats_all[:, : R * 4].contiguous()
+        sums_all = stats_all[:, R * 4:].contiguous()
+        loss_i, loss_t = compute.fwd_finish(row_part_all, sums_all, world, state)
+        ctx.saved = (img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset, state, sums_all)
+        ctx.meta = (group, compute, world, rank, b, logit_scale.dtype, logit_scale.shape)
+        return loss_i, loss_t
+
+    @staticmethod
+    def backward(ctx, g_i, g_t):
+        img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset, state, sums_all = ctx.saved
+        group, compute, world, rank, b, ls_dtype, ls_shape = ctx.meta
+        dev = txt_c.device
+        zero = torch.zeros(1, dtype=torch.float32, device=dev)
+        gi = zero if g_i is None else g_i.detach().to(torch.float32).reshape(1).contiguous()
+        gt = zero if g_t is None else g_t.detach().to(torch.float32).reshape(1).contiguous()
+        R_total = img_all.shape[0]
+        P_total = index_pos.numel() * world   # ranks hold equal shards
+        dtxt, dimg_hat, dls = compute.bwd_partial(img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset,
+                                                  gi, gt, R_total, P_total, state)
+        mine = torch.empty(b, dimg_hat.shape[1], dtype=torch.float32, device=dev)
+        _reduce_scatter_sum(mine, dimg_hat, rank, group)
+        dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)
+        dimg = compute.bwd_finish(img_all[rank * b:(rank + 1) * b], mine)
+        # every rank holds the same logit_scale parameter and DDP will AVERAGE its gradient over
+        # ranks (train.py:222-225); the loss is already the global mean, so hand DDP the full
+        # gradient on every rank (the average of identical values is the value itself)
+        return dimg, dtxt, dls.reshape(ls_shape).to(ls_dtype), None, None, None, None, None
+
+
+def global_contrastive(image_features, text_features, logit_scale, labels_per_image, labels_per_text,
+                       index_pos, group=None, compute=None):
+    """loss_i, loss_t over the GLOBAL batch; gradients for this rank's images and descriptions.
+
+    ``labels_per_image`` are global column indices, ``labels_per_text`` global row indices and
+    ``index_pos`` local column indices (see :func:`global_labels_for_rank`).
+    """
+    if compute is None:
+        compute = CudaBackend()
+    return _GlobalContrastive.apply(image_features, text_features, logit_scale, labels_per_image,
+                                    labels_per_text, index_pos, group, compute)
+
+
+def sharded_alignment(entitytxt_vec, object_vec, entitytxt_num, object_num, group=None, ot_fn=None):
+    """loss_ot = 0.01 * sum over the GLOBAL batch of the OT distance: local kernel + one scalar
+    all-reduce.  The gradient of the summed loss w.r.t. local nodes needs no exchange."""
+    fn = ot_fn if ot_fn is not None else F_.ot_alignment
+    loss, _ = fn(entitytxt_vec, object_vec, entitytxt_num, object_num)
+    total = loss.detach().clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    # value = global sum, gradient = local term (d total / d local nodes == d local loss / d local nodes)
+    return loss + (total - loss.detach())

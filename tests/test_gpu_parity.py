@@ -1,0 +1,321 @@
+"""Parity of the CUDA loss head (through the Python mirrors -> C ABI) against the oracle and the
+golden vectors generated from the unmodified reference.  Needs a B200: run with -m gpu.
+
+Tolerances (BASELINE.json north_star): fp32 mode loss 1e-5 relative (+2e-6 absolute for a CE loss,
+whose fp32 resolution is ulp(14.3) ~ 1e-6 however small the loss is); bf16 mode loss 2e-3,
+gradients 1e-2 (relative L2).  fp32-mode gradients are held to 2e-5 relative L2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+import clip_event_b200 as ce
+from clip_event_b200 import functional as F_
+from clip_event_b200 import synthetic as syn
+from oracle import clip_event_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+F32_LOSS_RTOL, F32_LOSS_ATOL, F32_GRAD = 1e-5, 2e-6, 2e-5
+BF16_LOSS_RTOL, BF16_GRAD = 2e-3, 1e-2
+
+
+def close(a, b, rtol, atol=0.0):
+    return abs(float(a) - float(b)) <= rtol * abs(float(b)) + atol
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def run_contrastive(img, txt, ls, lpi, lpt, idx, g_i=1.0, g_t=1.0):
+    """fp32 losses (functional layer, no output cast) + grads from the CUDA path."""
+    ig, tg = img.cuda().requires_grad_(True), txt.cuda().requires_grad_(True)
+    lsg = ls.cuda().requires_grad_(True)
+    li, lt = F_.contrastive_over_batch(ig, tg, lsg, lpi.cuda(), lpt.cuda(), idx.cuda())
+    (g_i * li + g_t * lt).backward()
+    torch.cuda.synchronize()
+    return li.item(), lt.item(), ig.grad.cpu(), tg.grad.cpu(), lsg.grad.item()
+
+
+def run_ot(txt, obj, tnum, onum, scale=1.0):
+    tg, og = txt.cuda().requires_grad_(True), obj.cuda().requires_grad_(True)
+    loss, dist = F_.ot_alignment(tg, og, tnum.cuda(), onum.cuda())
+    (scale * loss).backward()
+    torch.cuda.synchronize()
+    return loss.item(), dist.cpu(), tg.grad.cpu(), og.grad.cpu()
+
+
+# ------------------------------------------------------------------------------------------
+# golden vectors (reference outputs)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["contrastive_small_iid", "contrastive_small_trained",
+                                  "contrastive_small_randlabels"])
+def test_contrastive_golden_full(name):
+    g = load_golden(name)
+    li, lt, dimg, dtxt, dls = run_contrastive(_t(g["image_features"]), _t(g["text_features"]),
+                                              torch.tensor(syn.LOGIT_SCALE_INIT), _t(g["labels_per_image"]),
+                                              _t(g["labels_per_text"]), _t(g["index_pos"]))
+    assert close(li, g["loss_i"], F32_LOSS_RTOL, F32_LOSS_ATOL)
+    assert close(lt, g["loss_t"], F32_LOSS_RTOL, F32_LOSS_ATOL)
+    assert rel_err(dimg, g["dimg"]) < F32_GRAD
+    assert rel_err(dtxt, g["dtxt"]) < F32_GRAD
+    assert close(dls, g["dlogit_scale"], 1e-4, 1e-5)
+
+
+@pytest.mark.parametrize("name,kind", [("contrastive_c1_iid", "iid"), ("contrastive_c1_trained", "trained"),
+                                       ("contrastive_c2_trained", "trained")])
+def test_contrastive_golden_baseline_shapes(name, kind):
+    g = load_golden(name)
+    B, T, D, seed = int(g["B"]), int(g["T"]), int(g["D"]), int(g["seed"])
+    img, txt, ls = syn.contrastive_inputs(B, T, D, seed, kind)
+    li, lt, dimg, dtxt, dls = run_contrastive(img, txt, ls, _t(g["labels_per_image"]),
+                                              _t(g["labels_per_text"]), _t(g["index_pos"]))
+    assert close(li, g["loss_i"], F32_LOSS_RTOL, F32_LOSS_ATOL)
+    assert close(lt, g["loss_t"], F32_LOSS_RTOL, F32_LOSS_ATOL)
+    assert rel_err(dimg[:4], g["dimg_head"]) < F32_GRAD
+    assert rel_err(dtxt[:8], g["dtxt_head"]) < F32_GRAD
+    assert close(dimg.norm().item(), g["dimg_norm"], 1e-5)
+    assert close(dtxt.norm().item(), g["dtxt_norm"], 1e-5)
+
+
+@pytest.mark.parametrize("name", ["ot_small_full", "ot_small_edge", "ot_small_scattered", "ot_small_correlated"])
+def test_ot_golden_full(name):
+    g = load_golden(name)
+    loss, dist, dtxt, dobj = run_ot(_t(g["entitytxt_vec"]), _t(g["object_vec"]), _t(g["entitytxt_num"]),
+                                    _t(g["object_num"]))
+    assert close(loss, g["loss_ot"], F32_LOSS_RTOL, 1e-12)
+    assert rel_err(dist, g["dist"]) < F32_LOSS_RTOL
+    assert rel_err(dtxt, g["dtxt"]) < F32_GRAD
+    assert rel_err(dobj, g["dobj"]) < F32_GRAD
+    assert torch.isfinite(dtxt).all() and torch.isfinite(dobj).all()
+    assert (dobj[:, 0] == 0).all()
+
+
+@pytest.mark.parametrize("name,masks,kind", [("ot_c1_full", "full", "iid"), ("ot_c1_ragged", "ragged", "iid"),
+                                             ("ot_c2_edge", "edge", "iid"), ("ot_c2_correlated", "full", "correlated"),
+                                             ("ot_c4_ragged", "ragged", "iid"), ("ot_c5_corner", "full", "iid")])
+def test_ot_golden_baseline_shapes(name, masks, kind):
+    g = load_golden(name)
+    B, M, N, D, seed = (int(g[k]) for k in ("B", "M", "N", "D", "seed"))
+    txt, obj, tnum, onum = syn.ot_inputs(B, M, N, D, seed, masks, kind)
+    loss, dist, dtxt, dobj = run_ot(txt, obj, tnum, onum)
+    assert close(loss, g["loss_ot"], F32_LOSS_RTOL)
+    assert rel_err(dist, g["dist"]) < F32_LOSS_RTOL
+    assert rel_err(dtxt[:2, :4], g["dtxt_head"]) < F32_GRAD
+    assert rel_err(dobj[:2, :6], g["dobj_head"]) < F32_GRAD
+    assert close(dtxt.norm().item(), g["dtxt_norm"], 2e-5)
+    assert close(dobj.norm().item(), g["dobj_norm"], 2e-5)
+
+
+# ------------------------------------------------------------------------------------------
+# oracle on seeded inputs, both modes
+# ------------------------------------------------------------------------------------------
+CONTRASTIVE_CASES = [(6, 3, 32, "iid"), (9, 4, 40, "trained"), (32, 5, 512, "trained"),
+                     (256, 9, 512, "trained"), (256, 9, 512, "iid"), (130, 7, 768, "trained"),
+                     (1024, 9, 768, "trained")]
+
+
+@pytest.mark.parametrize("B,T,D,kind", CONTRASTIVE_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_contrastive_vs_oracle(B, T, D, kind, dtype):
+    img, txt, ls = syn.contrastive_inputs(B, T, D, 11, kind, dtype=dtype)
+    lpi, lpt, idx = syn.contrastive_labels(B, T)
+    ri, rt, rdi, rdt, rdls = orc.contrastive_closed_form(img.double(), txt.double(), ls.double(), lpi, lpt, idx,
+                                                         g_i=1.0, g_t=0.7)
+    li, lt, dimg, dtxt, dls = run_contrastive(img, txt, ls, lpi, lpt, idx, 1.0, 0.7)
+    if dtype == torch.float32:
+        assert close(li, ri, F32_LOSS_RTOL, F32_LOSS_ATOL) and close(lt, rt, F32_LOSS_RTOL, F32_LOSS_ATOL)
+        assert rel_err(dimg, rdi) < F32_GRAD and rel_err(dtxt, rdt) < F32_GRAD
+        assert close(dls, rdls, 1e-4, 1e-5)
+    else:
+        assert close(li, ri, BF16_LOSS_RTOL, 1e-4) and close(lt, rt, BF16_LOSS_RTOL, 1e-4)
+        assert rel_err(dimg, rdi) < BF16_GRAD and rel_err(dtxt, rdt) < BF16_GRAD
+        assert close(dls, rdls, 1e-2, 1e-3)
+
+
+def test_contrastive_arbitrary_labels_and_index_pos():
+    B, T, D = 40, 4, 64
+    img, txt, ls = syn.contrastive_inputs(B, T, D, 3, "iid")
+    g = torch.Generator().manual_seed(5)
+    lpi = torch.randint(0, B * T, (B,), generator=g)
+    lpt = torch.randint(0, B, (B * T,), generator=g)
+    idx = torch.randperm(B * T, generator=g)[:B].sort().values
+    ri, rt, rdi, rdt, rdls = orc.contrastive_closed_form(img.double(), txt.double(), ls.double(), lpi, lpt, idx)
+    li, lt, dimg, dtxt, dls = run_contrastive(img, txt, ls, lpi, lpt, idx)
+    assert close(li, ri, F32_LOSS_RTOL, F32_LOSS_ATOL) and close(lt, rt, F32_LOSS_RTOL, F32_LOSS_ATOL)
+    assert rel_err(dimg, rdi) < F32_GRAD and rel_err(dtxt, rdt) < F32_GRAD
+
+
+OT_CASES = [(4, 4, 7, 16, "full", "iid"), (6, 5, 9, 24, "edge", "iid"), (5, 6, 11, 16, "scattered", "iid"),
+            (32, 8, 50, 512, "ragged", "iid"), (16, 16, 50, 512, "full", "correlated"),
+            (8, 32, 257, 768, "ragged", "iid"), (2, 64, 577, 768, "full", "iid"), (3, 20, 300, 64, "ragged", "iid"),
+            (3, 64, 130, 64, "ragged", "correlated"), (3, 32, 577, 64, "edge", "iid"), (3, 4, 197, 64, "ragged", "iid")]
+
+
+@pytest.mark.parametrize("B,M,N,D,masks,kind", OT_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ot_vs_oracle(B, M, N, D, masks, kind, dtype):
+    txt, obj, tnum, onum = syn.ot_inputs(B, M, N, D, 13, masks, kind, dtype=dtype)
+    tp, ip = tnum == 0, onum[:, 1:] == 0
+    d_ref, dx_ref, dy_ref = orc.ot_closed_form_grads(txt.double(), obj.double()[:, 1:], tp, ip,
+                                                     torch.full((B,), 0.01, dtype=torch.float64))
+    loss, dist, dtxt, dobj = run_ot(txt, obj, tnum, onum)
+    if dtype == torch.float32:
+        assert close(loss, 0.01 * d_ref.sum().item(), F32_LOSS_RTOL)
+        assert rel_err(dist, d_ref) < F32_LOSS_RTOL
+        assert rel_err(dtxt, dx_ref) < F32_GRAD and rel_err(dobj[:, 1:], dy_ref) < F32_GRAD
+    else:
+        assert close(loss, 0.01 * d_ref.sum().item(), BF16_LOSS_RTOL)
+        assert rel_err(dtxt, dx_ref) < BF16_GRAD and rel_err(dobj[:, 1:], dy_ref) < BF16_GRAD
+    assert (dobj[:, 0] == 0).all() and torch.isfinite(dtxt).all() and torch.isfinite(dobj).all()
+    empty = (tp.all(1) | ip.all(1))
+    assert (dist[empty] == 0).all()                       # model_ot.py:62: empty node set -> distance 0
+
+
+def test_ot_upstream_gradient_scaling_and_per_sample_path():
+    txt, obj, tnum, onum = syn.ot_inputs(6, 8, 20, 64, 2, "ragged")
+    _, _, d1, o1 = run_ot(txt, obj, tnum, onum, scale=1.0)
+    _, _, d3, o3 = run_ot(txt, obj, tnum, onum, scale=-2.5)
+    assert rel_err(d3, -2.5 * d1) < 1e-6 and rel_err(o3, -2.5 * o1) < 1e-6
+    # optimal_transport_dist: per-sample distances with per-sample upstream gradients
+    tp, ip = (tnum == 0).cuda(), (onum[:, 1:] == 0).cuda()
+    tg = txt.cuda().requires_grad_(True)
+    og = obj[:, 1:].contiguous().cuda().requires_grad_(True)
+    dist = ce.optimal_transport_dist(tg, og, tp, ip)
+    wts = torch.linspace(0.5, 2.0, 6).cuda()
+    (dist * wts).sum().backward()
+    d_ref, dx_ref, dy_ref = orc.ot_closed_form_grads(txt.double(), obj.double()[:, 1:], tp.cpu(), ip.cpu(), wts.cpu().double())
+    assert rel_err(dist.cpu(), d_ref) < F32_LOSS_RTOL
+    assert rel_err(tg.grad.cpu(), dx_ref) < F32_GRAD and rel_err(og.grad.cpu(), dy_ref) < F32_GRAD
+
+
+def test_ot_second_backward_raises():
+    txt, obj, tnum, onum = syn.ot_inputs(2, 4, 6, 16, 0, "full")
+    tg = txt.cuda().requires_grad_(True)
+    loss, _ = F_.ot_alignment(tg, obj.cuda(), tnum.cuda(), onum.cuda())
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()
+
+
+# ------------------------------------------------------------------------------------------
+# the reference-granularity blocks
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ot_small_full", "ot_small_edge", "ot_small_scattered"])
+def test_ot_blocks_golden(name):
+    g = load_golden(name)
+    txt, obj = _t(g["entitytxt_vec"]), _t(g["object_vec"])
+    tnum, onum = _t(g["entitytxt_num"]), _t(g["object_num"])
+    tp, ip = tnum == 0, onum[:, 1:] == 0
+    img = obj[:, 1:].contiguous()
+    cost = ce.cost_matrix_cosine(txt.cuda(), img.cuda())
+    assert rel_err(cost.cpu(), g["cost"]) < 2e-6
+    jp = tp.unsqueeze(-1) | ip.unsqueeze(-2)
+    cm = _t(g["cost"]).masked_fill(jp, 0).cuda()
+    tl = (tp.size(1) - tp.sum(1)).float().cuda()
+    il = (ip.size(1) - ip.sum(1)).float().cuda()
+    plan = ce.ipot(cm, tl, tp.cuda(), il, ip.cuda(), jp.cuda(), 0.5, 50, 1)
+    assert rel_err(plan.cpu(), g["plan"]) < 1e-5
+    plan2 = ce.ipot(cm, tl, tp.cuda(), il, ip.cuda(), jp.cuda(), 0.3, 10, 1)
+    assert rel_err(plan2.cpu(), g["plan_b03_it10"]) < 1e-5
+    tr = ce.trace(cm.matmul(plan))
+    assert rel_err(tr.cpu(), g["trace"]) < 1e-5
+    dist = ce.optimal_transport_dist(txt.cuda(), img.cuda(), tp.cuda(), ip.cuda())
+    assert rel_err(dist.cpu(), g["dist"]) < F32_LOSS_RTOL
+    dist_c = ce.optimal_transport_dist(txt.cuda(), img.cuda(), tp.cuda(), ip.cuda(), cost=_t(g["cost"]).cuda())
+    assert rel_err(dist_c.cpu(), g["dist"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["contrastive_small_iid", "contrastive_small_trained"])
+def test_materialised_logits_golden(name):
+    g = load_golden(name)
+    head = ce.ClipEventHead().cuda()
+    lpi, lpt = head(_t(g["image_features"]).cuda(), _t(g["text_features"]).cuda())
+    assert tuple(lpi.shape) == g["logits_per_image"].shape and tuple(lpt.shape) == g["logits_per_text"].shape
+    assert rel_err(lpi.materialize().cpu(), g["logits_per_image"]) < 1e-5
+    assert rel_err(lpt.materialize().cpu(), g["logits_per_text"]) < 1e-5
+    # preprocess_description_contrastive.py:129-131 style consumer
+    probs = lpi.softmax(dim=-1)
+    assert rel_err(probs.cpu(), _t(g["logits_per_image"]).softmax(-1)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------
+# the drop-in modules as engine.py drives them, BASELINE shapes, plus size-independent properties
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wl,dtype", [("c1", torch.float32), ("c2", torch.float32), ("c2", torch.bfloat16)])
+def test_engine_style_step(wl, dtype):
+    w = syn.WORKLOADS[wl]
+    img, txt, ls = syn.contrastive_inputs(w.B, w.T, w.D, 0, "trained", dtype=dtype)
+    lpi, lpt, idx = syn.contrastive_labels(w.B, w.T)
+    etxt, obj, tnum, onum = syn.ot_inputs(w.B, w.M, w.N, w.D, 0, "ragged", dtype=dtype)
+    ref_losses, ref_grads = orc.loss_head_step(img.float(), txt.float(), ls, lpi, lpt, idx, etxt.float(),
+                                               obj.float(), tnum, onum)
+    head = ce.ClipEventHead().cuda()
+    criterion, criterion_ot = ce.CriterionContrastive("ce"), ce.CriterionAlignment()
+    leaves = {k: v.cuda().requires_grad_(True) for k, v in dict(img=img, txt=txt, etxt=etxt, obj=obj).items()}
+    a, b = head(leaves["img"], leaves["txt"])                                               # engine.py:48
+    loss_dict = criterion(a, b, lpi.cuda(), lpt.cuda(), index_pos=idx.cuda(),
+                          constrastive_overbatch=head.constrastive_overbatch)               # engine.py:52-53
+    loss_dict.update(criterion_ot(leaves["etxt"], leaves["obj"], tnum.cuda(), onum.cuda()))  # engine.py:63
+    losses = sum(loss for loss in loss_dict.values())                                       # engine.py:67
+    losses.backward()                                                                       # engine.py:88
+    torch.cuda.synchronize()
+    lt, gt = (F32_LOSS_RTOL, F32_GRAD) if dtype == torch.float32 else (4e-3, BF16_GRAD)   # bf16 OUTPUT cast: 2^-8
+    for k in ("loss_i", "loss_t", "loss_ot"):
+        assert loss_dict[k].dtype == dtype
+        assert close(loss_dict[k].item(), ref_losses[k].item(), lt, 2e-6 if dtype == torch.float32 else 1e-4), k
+    for mine, theirs in [("img", "image_features"), ("txt", "text_features"), ("etxt", "entitytxt_vec"),
+                         ("obj", "object_vec")]:
+        assert rel_err(leaves[mine].grad.cpu(), ref_grads[theirs]) < gt, mine
+    assert close(head.logit_scale.grad.item(), ref_grads["logit_scale"].item(), 1e-2 if dtype != torch.float32 else 1e-4, 1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_full_size_properties(dtype):
+    """c4-sized inputs: properties that hold without running the oracle at full size."""
+    w = syn.WORKLOADS["c4"]
+    B = 256
+    img, txt, ls = syn.contrastive_inputs(B, w.T, w.D, 1, "trained", dtype=dtype)
+    lpi, lpt, idx = syn.contrastive_labels(B, w.T)
+    li, lt, dimg, dtxt, dls = run_contrastive(img, txt, ls, lpi, lpt, idx)
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    # the loss is invariant to the scale of each embedding => gradient orthogonal to the embedding
+    cosi = (dimg.double() * img.double()).sum(1) / (dimg.double().norm(dim=1) * img.double().norm(dim=1) + 1e-30)
+    cost = (dtxt.double() * txt.double()).sum(1) / (dtxt.double().norm(dim=1) * txt.double().norm(dim=1) + 1e-30)
+    assert cosi.abs().max() < tol and cost.abs().max() < tol
+    assert li >= 0 and lt >= 0
+    # permuting the samples of the OT batch permutes the distances and leaves the loss unchanged
+    etxt, obj, tnum, onum = syn.ot_inputs(64, w.M, w.N, w.D, 2, "ragged", dtype=dtype)
+    loss, dist, dt_, do_ = run_ot(etxt, obj, tnum, onum)
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(0))
+    loss_p, dist_p, dtp, dop = run_ot(etxt[perm], obj[perm], tnum[perm], onum[perm])
+    assert torch.equal(dist_p, dist[perm]) and torch.equal(dtp, dt_[perm]) and torch.equal(dop, do_[perm])
+    assert close(loss_p, loss, 1e-6)
+    # padded nodes receive exactly zero gradient; scale invariance of the cosine cost again
+    assert (dt_[tnum == 0] == 0).all() and (do_[onum == 0] == 0).all()
+    valid = tnum == 1
+    c = (dt_.double() * etxt.double()).sum(-1)[valid] / (dt_.double().norm(dim=-1)[valid] * etxt.double().norm(dim=-1)[valid] + 1e-30)
+    assert c.abs().max() < (1e-3 if dtype == torch.float32 else 5e-2)
+    assert (dist >= -1e-6).all()
+
+
+def test_error_behaviour_on_gpu():
+    head = ce.ClipEventHead().cuda()
+    crit = ce.CriterionContrastive("ce")
+    a, b = head(torch.randn(4, 16, device="cuda"), torch.randn(8, 16, device="cuda"))
+    with pytest.raises(RuntimeError):
+        crit(a, b, index_pos=None)
+    with pytest.raises(RuntimeError):     # fp16 is not a supported embedding dtype
+        F_.contrastive_over_batch(torch.randn(4, 16, device="cuda").half(), torch.randn(8, 16, device="cuda").half(),
+                                  torch.tensor(1.0, device="cuda"), torch.arange(4).cuda(), torch.arange(8).cuda(),
+                                  torch.arange(4).cuda())
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        F_.contrastive_over_batch(torch.randn(4, 12, device="cuda"), torch.randn(8, 12, device="cuda"),
+                                  torch.tensor(1.0, device="cuda"), torch.arange(4).cuda(), torch.arange(8).cuda() // 2,
+                                  torch.arange(4).cuda() * 2)
+    with pytest.raises(RuntimeError):     # more than 64 text nodes
+        ce.CriterionAlignment()(torch.randn(2, 65, 16, device="cuda"), torch.randn(2, 9, 16, device="cuda"),
+                                torch.ones(2, 65, dtype=torch.int64, device="cuda"),
+                                torch.ones(2, 9, dtype=torch.int64, device="cuda"))
