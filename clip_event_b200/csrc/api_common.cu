@@ -23,6 +23,9 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 static thread_local int g_dev_checked = -1;  // device ordinal that passed the check
 static thread_local int g_sms = 0;
 
@@ -92,3 +95,4 @@ int make_tmap(CUtensorMap* out, const void* ptr, bool fp32, uint64_t inner, uint
 extern "C" int ce_version(void) { return 100; }
 extern "C" const char* ce_last_error(void) { return ce::g_err; }
 extern "C" int ce_device_check(void) { return ce::check_device(); }
+extern "C" unsigned long long ce_debug_launch_count(void) { return ce::g_launches; }

@@ -29,8 +29,11 @@ int num_sms();
     }                                                                                          \
   } while (0)
 
+void count_launch();  // bumps the per-process kernel-launch counter (ce_debug_launch_count)
+
 #define CE_LAUNCH_CHECK()                                                                      \
   do {                                                                                         \
+    ::ce::count_launch();                                                                      \
     cudaError_t _e = cudaGetLastError();                                                       \
     if (_e != cudaSuccess) {                                                                   \
       ::ce::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

@@ -168,12 +168,12 @@ class _OtAlignment(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, g_dist):
-        dtxt, dobj = ctx.stash
-        if dtxt is None:
-            return (None,) * 9
         if ctx.consumed:
             raise RuntimeError("clip_event_b200 OT: backward through the stashed gradients a second time; "
                                "run the forward again (retain_graph is not supported on this path)")
+        dtxt, dobj = ctx.stash
+        if dtxt is None:
+            return (None,) * 9
         ctx.consumed = True
         ctx.stash = (None, None)
         dev = dtxt.device

@@ -176,6 +176,9 @@ int ce_ot_trace(const float* x, int B, int n, float* out, ce_stream_t stream);
 int ce_scale_inplace(void* x, int64_t rows, int64_t row_len, int64_t row_stride, int dtype,
                      const float* g, ce_stream_t stream);
 
+/* Number of kernels this library has launched in this process (for benchmark bookkeeping). */
+unsigned long long ce_debug_launch_count(void);
+
 /* Debug / self-test: C[M,N] (fp32) = A * B^t through the same tcgen05 + TMA main loop the
  * similarity GEMM uses.  a_mn_major / b_mn_major select the operand layouts:
  *   K-major : A is [M, K] row-major, B is [N, K] row-major

@@ -314,3 +314,41 @@ def loss_head_step(image_features, text_features, logit_scale, labels_per_image,
 def ln_inv_temperature() -> float:
     """model_clip.py:330  logit_scale init = ln(1/0.07)."""
     return math.log(1 / 0.07)
+
+
+# --------------------------------------------------------------------------- #
+# Bounded CPU sample of a large workload (bench.py cpu_baseline / --impl reference)
+# --------------------------------------------------------------------------- #
+
+
+def loss_head_rowblock_step(image_features, text_features, logit_scale, descs_per_image, rows,
+                            entitytxt_vec=None, object_vec=None, entitytxt_num=None, object_num=None):
+    """fwd+bwd of the reference loss head for a BLOCK of ``rows`` images of a larger batch.
+
+    Per-image work is what the full batch costs per image: the block's images are scored against
+    ALL B*T descriptions (image-side CE, model_clip.py:506-508,648) and the block's positive
+    descriptions against ALL B images (text-side CE, model_clip.py:504,655-659), with the
+    reference's own op sequence (normalise, exp, matmul, CrossEntropyLoss, autograd backward);
+    the OT criterion runs on the block's samples.  Returns the summed loss (a float).
+    """
+    T = descs_per_image
+    lo, hi = rows
+    img = image_features.detach().clone().requires_grad_(True)
+    txt = text_features.detach().clone().requires_grad_(True)
+    ls = logit_scale.detach().clone().requires_grad_(True)
+    img_n = img / img.norm(dim=-1, keepdim=True)
+    txt_n = txt / txt.norm(dim=-1, keepdim=True)
+    s = ls.exp()
+    ce = torch.nn.CrossEntropyLoss()
+    logits_per_image = s * img_n[lo:hi] @ txt_n.t()                                  # [rows, B*T]
+    labels_i = torch.arange(lo, hi) * T
+    pos = torch.arange(lo, hi) * T
+    logits_per_text = s * txt_n.index_select(0, pos) @ img_n.t()                     # [rows, B]
+    labels_t = torch.arange(lo, hi)
+    total = ce(logits_per_image, labels_i) + ce(logits_per_text, labels_t)
+    if entitytxt_vec is not None:
+        e = entitytxt_vec[lo:hi].detach().clone().requires_grad_(True)
+        o = object_vec[lo:hi].detach().clone().requires_grad_(True)
+        total = total + alignment_criterion(e, o, entitytxt_num[lo:hi], object_num[lo:hi])["loss_ot"]
+    total.backward()
+    return float(total.detach())
