@@ -17,9 +17,6 @@
 namespace ce {
 namespace {
 
-constexpr int kDC = 32;        // embedding columns staged per step
-constexpr int kLdA = kDC + 4;  // smem row stride (floats) for operands read along K  (== 4 mod 32)
-constexpr int kLdB = kDC + 8;  // smem row stride for operands read across K          (== 8 mod 32)
 
 struct OtArgs {
   const void* txt;
@@ -55,39 +52,73 @@ __device__ __forceinline__ void mma_split(float* acc, const uint32_t* ahi, const
   mma_tf32(acc, ahi, bhi);
 }
 
-// Stage `rows` rows x kDC columns (starting at column d0) of a [*, D] matrix into smem as fp32.
-template <int DT, int LD>
-__device__ __forceinline__ void stage_rows(float* dst, const typename In<DT>::type* src, int rows,
-                                           int rows_valid, int D, int d0, int nthreads) {
-  constexpr int V = In<DT>::kVec;
-  constexpr int G = kDC / V;  // 16-byte groups per row
-  for (int idx = threadIdx.x; idx < rows * G; idx += nthreads) {
-    int r = idx / G, c = (idx % G) * V;
-    float v[8];
-    if (r < rows_valid && d0 + c < D) {
-      In<DT>::load16(src + (int64_t)r * D + d0 + c, v);
-    } else {
-#pragma unroll
-      for (int i = 0; i < V; ++i) v[i] = 0.f;
-    }
-    float4* p = reinterpret_cast<float4*>(dst + r * LD + c);
-    p[0] = make_float4(v[0], v[1], v[2], v[3]);
-    if constexpr (V == 8) p[1] = make_float4(v[4], v[5], v[6], v[7]);
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// B fragment (k16 x n8) of a row-major [k][n] bf16 tile: two transposed 8x8 loads.
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t* r, const void* row_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r[0]), "=r"(r[1])
+               : "r"(smem_u32(row_ptr)));
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ---- cp.async ring: every stage holds one 128-byte column slab of [x rows | y rows] ----------
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kSlabBytes = 128;   // bytes of one row staged per step (32 fp32 / 64 bf16 columns)
+constexpr int kStages = 3;
+
+// Stage slab `c` of the MP text rows followed by `rows` image rows; RS = smem row stride in bytes.
+template <int RS>
+__device__ __forceinline__ void issue_slab(uint8_t* stage, const uint8_t* xg, const uint8_t* yg,
+                                           int MP, int M, int rows, int rows_valid, int row_bytes,
+                                           int c, int nthreads) {
+  const int total = (MP + rows) * (kSlabBytes / 16);
+  const int col0 = c * kSlabBytes;
+  for (int idx = threadIdx.x; idx < total; idx += nthreads) {
+    const int r = idx >> 3, piece = (idx & 7) * 16;
+    const bool is_x = r < MP;
+    const int rr = is_x ? r : r - MP;
+    const bool valid = (is_x ? rr < M : rr < rows_valid) && (col0 + piece < row_bytes);
+    const uint8_t* src = (is_x ? xg : yg) + (valid ? (int64_t)rr * row_bytes + col0 + piece : 0);
+    cp_async16(stage + r * RS + piece, src, valid);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // Kernel A: S = y x^t (raw), row sums of squares.
 // grid (B, nsplit); CTA handles image-node tiles [ns*tiles_per_cta, ...); warp w owns tiles
-// w, w+NWARPS, ...; text nodes (padded to MP) sit on the mma N axis.
+// w, w+NWARPS, ...; text nodes (padded to MP) sit on the mma N axis.  Inputs stream through a
+// 3-stage cp.async ring in their own dtype: bf16 feeds m16n8k16 bf16 mma directly, fp32 feeds
+// the 3xTF32 path.
 // ------------------------------------------------------------------------------------------
+constexpr int kRsA = kSlabBytes + 16;   // 36 words: conflict-free fragment reads along K
+
 template <int DT, int MP, int NWARPS, int TPW>
 __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
-  constexpr int NSPLIT = (DT == CE_F32) ? 3 : 1;
+  constexpr bool F32 = DT == CE_F32;
   constexpr int NT = NWARPS * 32;
   constexpr int NJ = MP / 8;
-  using T = typename In<DT>::type;
-  extern __shared__ __align__(16) float smem[];
+  constexpr int RSW = kRsA / 4;               // row stride in 32-bit words
+  constexpr int ESZ = F32 ? 4 : 2;
+  extern __shared__ __align__(16) uint8_t smem_a[];
   const int b = blockIdx.x, ns = blockIdx.y;
   const int ntiles = (a.N + 15) / 16;
   const int tile0 = ns * a.tiles_per_cta;
@@ -95,11 +126,12 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
   const int row0 = tile0 * 16;
   const int rows = my_tiles * 16;
   const int rows_valid = min(rows, a.N - row0);
-  float* xs = smem;             // [MP][kLdA]
-  float* ys = smem + MP * kLdA; // [rows][kLdA]
-  const T* xg = reinterpret_cast<const T*>(a.txt) + (int64_t)b * a.txt_bs;
-  const T* yg = reinterpret_cast<const T*>(a.img) + (int64_t)b * a.img_bs + (int64_t)row0 * a.D;
+  const int stage_bytes = (MP + rows) * kRsA;
+  const int row_bytes = a.D * ESZ;
+  const uint8_t* xg = reinterpret_cast<const uint8_t*>(a.txt) + (int64_t)b * a.txt_bs * ESZ;
+  const uint8_t* yg = reinterpret_cast<const uint8_t*>(a.img) + ((int64_t)b * a.img_bs + (int64_t)row0 * a.D) * ESZ;
   const int w = warp_id(), lane = lane_id(), g = lane >> 2, t = lane & 3;
+  const int nslab = (row_bytes + kSlabBytes - 1) / kSlabBytes;
 
   float acc[TPW][NJ][4];
   float yss[TPW][2];
@@ -115,15 +147,26 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
 #pragma unroll
   for (int j = 0; j < NJ; ++j) xss[j] = 0.f;
 
-  for (int d0 = 0; d0 < a.D; d0 += kDC) {
-    stage_rows<DT, kLdA>(xs, xg, MP, a.M, a.D, d0, NT);
-    stage_rows<DT, kLdA>(ys, yg, rows, rows_valid, a.D, d0, NT);
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) {
+    if (s < nslab) issue_slab<kRsA>(smem_a + s * stage_bytes, xg, yg, MP, a.M, rows, rows_valid, row_bytes, s, NT);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nslab; ++c) {
+    {
+      const int cn = c + kStages - 1;
+      if (cn < nslab) issue_slab<kRsA>(smem_a + (cn % kStages) * stage_bytes, xg, yg, MP, a.M, rows, rows_valid, row_bytes, cn, NT);
+      cp_async_commit();
+    }
+    cp_async_wait<kStages - 1>();
     __syncthreads();
-    if constexpr (NSPLIT == 3) {
+    const uint32_t* xs = reinterpret_cast<const uint32_t*>(smem_a + (c % kStages) * stage_bytes);
+    const uint32_t* ys = xs + MP * RSW;
+    if constexpr (F32) {
       // fp32 mode.  The tensor core truncates its fp32 accumulator after every instruction, a bias
       // that grows with the accumulator's magnitude and the chain length (measured: ~4e-6
       // relative over D = 512) and that IPOT then amplifies by iters/beta.  So each 32-column
-      // step is accumulated from zero (12 instructions, small partial sums) and folded into the
+      // slab is accumulated from zero (12 instructions, small partial sums) and folded into the
       // running sum with an ordinary round-to-nearest add.
 #pragma unroll
       for (int i = 0; i < TPW; ++i) {
@@ -133,61 +176,61 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
 #pragma unroll
           for (int j = 0; j < NJ; ++j)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tacc[j][c] = 0.f;
+            for (int cc = 0; cc < 4; ++cc) tacc[j][cc] = 0.f;
 #pragma unroll
-          for (int ks = 0; ks < kDC / 8; ++ks) {
-            const float* yr = ys + (tile * 16 + g) * kLdA + ks * 8 + t;
-            float av[4] = {yr[0], yr[8 * kLdA], yr[4], yr[8 * kLdA + 4]};
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t* yr = ys + (tile * 16 + g) * RSW + ks * 8 + t;
+            float av[4] = {__uint_as_float(yr[0]), __uint_as_float(yr[8 * RSW]), __uint_as_float(yr[4]),
+                           __uint_as_float(yr[8 * RSW + 4])};
             yss[i][0] += av[0] * av[0] + av[2] * av[2];
             yss[i][1] += av[1] * av[1] + av[3] * av[3];
             uint32_t ahi[4], alo[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) split_tf32<NSPLIT>(av[c], ahi[c], alo[c]);
+            for (int cc = 0; cc < 4; ++cc) split_tf32<3>(av[cc], ahi[cc], alo[cc]);
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-              float b0 = xs[(8 * j + g) * kLdA + ks * 8 + t];
-              float b1 = xs[(8 * j + g) * kLdA + ks * 8 + t + 4];
+              float b0 = __uint_as_float(xs[(8 * j + g) * RSW + ks * 8 + t]);
+              float b1 = __uint_as_float(xs[(8 * j + g) * RSW + ks * 8 + t + 4]);
               if (i == 0) xss[j] += b0 * b0 + b1 * b1;
               uint32_t bhi[2], blo[2];
-              split_tf32<NSPLIT>(b0, bhi[0], blo[0]);
-              split_tf32<NSPLIT>(b1, bhi[1], blo[1]);
-              mma_split<NSPLIT>(tacc[j], ahi, alo, bhi, blo);
+              split_tf32<3>(b0, bhi[0], blo[0]);
+              split_tf32<3>(b1, bhi[1], blo[1]);
+              mma_split<3>(tacc[j], ahi, alo, bhi, blo);
             }
           }
 #pragma unroll
           for (int j = 0; j < NJ; ++j)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[i][j][c] += tacc[j][c];
+            for (int cc = 0; cc < 4; ++cc) acc[i][j][cc] += tacc[j][cc];
         }
       }
     } else {
+      // bf16 mode: products of bf16 inputs are exact in the fp32 accumulator
 #pragma unroll
-    for (int ks = 0; ks < kDC / 8; ++ks) {
-      uint32_t bhi[NJ][2], blo[NJ][2];
+      for (int ks = 0; ks < 4; ++ks) {          // 4 x k16 per 64-column slab
+        uint32_t bf[NJ][2];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        float b0 = xs[(8 * j + g) * kLdA + ks * 8 + t];
-        float b1 = xs[(8 * j + g) * kLdA + ks * 8 + t + 4];
-        xss[j] += b0 * b0 + b1 * b1;
-        split_tf32<NSPLIT>(b0, bhi[j][0], blo[j][0]);
-        split_tf32<NSPLIT>(b1, bhi[j][1], blo[j][1]);
-      }
+        for (int j = 0; j < NJ; ++j) {
+          bf[j][0] = xs[(8 * j + g) * RSW + ks * 8 + t];
+          bf[j][1] = xs[(8 * j + g) * RSW + ks * 8 + t + 4];
+          float p0 = bf_lo(bf[j][0]), p1 = bf_hi(bf[j][0]), p2 = bf_lo(bf[j][1]), p3 = bf_hi(bf[j][1]);
+          xss[j] += p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3;
+        }
 #pragma unroll
-      for (int i = 0; i < TPW; ++i) {
-        int tile = w + i * NWARPS;
-        if (tile < my_tiles) {
-          const float* yr = ys + (tile * 16 + g) * kLdA + ks * 8 + t;
-          float av[4] = {yr[0], yr[8 * kLdA], yr[4], yr[8 * kLdA + 4]};
-          yss[i][0] += av[0] * av[0] + av[2] * av[2];
-          yss[i][1] += av[1] * av[1] + av[3] * av[3];
-          uint32_t ahi[4], alo[4];
+        for (int i = 0; i < TPW; ++i) {
+          int tile = w + i * NWARPS;
+          if (tile < my_tiles) {
+            const uint32_t* yr = ys + (tile * 16 + g) * RSW + ks * 8 + t;
+            uint32_t af[4] = {yr[0], yr[8 * RSW], yr[4], yr[8 * RSW + 4]};
+            yss[i][0] += bf_lo(af[0]) * bf_lo(af[0]) + bf_hi(af[0]) * bf_hi(af[0]) +
+                         bf_lo(af[2]) * bf_lo(af[2]) + bf_hi(af[2]) * bf_hi(af[2]);
+            yss[i][1] += bf_lo(af[1]) * bf_lo(af[1]) + bf_hi(af[1]) * bf_hi(af[1]) +
+                         bf_lo(af[3]) * bf_lo(af[3]) + bf_hi(af[3]) * bf_hi(af[3]);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) split_tf32<NSPLIT>(av[c], ahi[c], alo[c]);
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) mma_split<NSPLIT>(acc[i][j], ahi, alo, bhi[j], blo[j]);
+            for (int j = 0; j < NJ; ++j) mma_bf16(acc[i][j], af, bf[j]);
+          }
         }
       }
-    }
     }
     __syncthreads();
   }
@@ -254,69 +297,81 @@ __device__ __forceinline__ bool node_is_pad(const void* mask, int kind, int64_t 
   return reinterpret_cast<const uint8_t*>(mask)[idx] != 0;
 }
 
-template <int MP, int RPT>
-__global__ void __launch_bounds__(256) ot_ipot_kernel(IpotArgs a) {
-  constexpr int TC = MP / 4;       // threads per row
-  constexpr int RP = 256 / TC;     // rows per pass
-  constexpr int RW = 32 / TC;      // rows per warp per pass
-  __shared__ float s_rx[MP], s_sigma[MP], s_xguard[MP];
-  __shared__ float s_red[8][MP];
-  __shared__ float s_cnt[2];
-  __shared__ float s_red2[8];
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int tc = tid % TC, tr = tid / TC;
+// The plan is carried in factorised form T = diag(u) R diag(v): with Q = A*T the reference
+// recurrence (model_ot.py:55-61)
+//     delta = 1/(y_len * Q sigma + y_guard);  sigma' = 1/(x_len * Q^t delta + x_guard);  T' = delta*Q*sigma'
+// becomes R1 = A*R (1 mul / element), rowdot = R1 (v*sigma) (1 fma), coldot = R1^t (delta*u) (1 fma),
+// u' = delta*u, v' = v*sigma'  -- 3 element-wise operations per iteration instead of 5, issued as
+// packed f32x2 instructions.  Every kRefold iterations u and v are folded back into R so that R
+// (which shrinks like A^t) stays far from the fp32 underflow range.
+constexpr int kRefold = 4;
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+// One launch geometry for both solvers:
+//   G    threads cooperating on one sample (32: one warp, no block barrier; 256: one CTA)
+//   TC   = MP/4 threads across a row, each owning 4 consecutive text nodes (two float2)
+//   RP   = G/TC image rows per pass, RPT passes
+template <int MP, int RPT, int G>
+__global__ void __launch_bounds__((G < 256 ? 256 : G)) ot_ipot_kernel(IpotArgs a) {
+  constexpr int TC = MP / 4;
+  constexpr int RP = G / TC;
+  constexpr int BT = G < 256 ? 256 : G;   // threads per CTA
+  constexpr int SPC = BT / G;             // samples per CTA
+  constexpr int NW = G / 32;          // warps per sample
+  static_assert(TC <= 32 && RP >= 1, "layout");
+  __shared__ __align__(16) float s_red[2][NW][MP];   // column partials (G == 256 only)
+  __shared__ float s_cnt[SPC][2];
+  __shared__ float s_red2[NW];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int sub = tid / G;                       // sample slot inside the CTA
+  const int gt = tid % G;                        // thread inside the sample group
+  const int w = gt >> 5;                         // warp inside the sample group
+  const int b = blockIdx.x * SPC + sub;
+  const bool live = b < a.B;
+  const int bb = live ? b : 0;
+  const int tc = gt % TC, tr = gt / TC;
   const int m0 = tc * 4;
+  auto group_sync = [&]() { if constexpr (G == 32) __syncwarp(); else __syncthreads(); };
 
-  // ---- masks, lengths, norms --------------------------------------------------------------
-  if (tid < MP) {
-    bool pad = tid >= a.M || node_is_pad(a.txt_mask, a.mask_kind, (int64_t)b * a.txt_ms + tid);
-    float n2 = a.nx2[(int64_t)b * MP + tid];
-    s_rx[tid] = 1.f / fmaxf(sqrtf(n2), a.eps);
-    s_xguard[tid] = pad ? 1e4f : 0.f;
-  }
-  if (tid < 2) s_cnt[tid] = 0.f;
-  __syncthreads();
-  float ry[RPT], yguard[RPT];
-  {
-    float cnt = 0.f;
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      int n = tr + i * RP;
-      bool pad = n >= a.N || node_is_pad(a.img_mask, a.mask_kind, (int64_t)b * a.img_ms + n);
-      float n2 = n < a.N ? a.ny2[(int64_t)b * a.Nld + n] : 1.f;
-      ry[i] = 1.f / fmaxf(sqrtf(n2), a.eps);
-      yguard[i] = pad ? 1e4f : 0.f;
-      if (tc == 0 && !pad) cnt += 1.f;
-    }
-    cnt = warp_sum(cnt);
-    if (lane == 0 && cnt != 0.f) atomicAdd(&s_cnt[1], cnt);
-    if (tid < MP && s_xguard[tid] == 0.f) atomicAdd(&s_cnt[0], 1.f);
-  }
-  __syncthreads();
-  const float xlen = s_cnt[0], ylen = s_cnt[1];
-  float* Sg = a.S + (int64_t)b * a.N * MP;
-
-  if (xlen == 0.f || ylen == 0.f) {
-    // model_ot.py:62 -- the final mask zeroes the whole plan: distance 0, gradient 0
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      int n = tr + i * RP;
-      if (n < a.N) {
-        *reinterpret_cast<float4*>(Sg + (int64_t)n * MP + m0) = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tc == 0) a.ny2[(int64_t)b * a.Nld + n] = 0.f;
-      }
-    }
-    if (tid < MP) a.nx2[(int64_t)b * MP + tid] = 0.f;
-    if (tid == 0) a.dist[b] = 0.f;
-    return;
-  }
-
-  // ---- kernel matrix A = exp(-C/beta), plan T = 1 (0 at joint pads) -----------------------
-  float A[RPT][4], T[RPT][4];
+  // ---- masks, lengths, inverse norms -------------------------------------------------------
   float rx[4], xg[4];
+  float xcount = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { rx[j] = s_rx[m0 + j]; xg[j] = s_xguard[m0 + j]; }
+  for (int j = 0; j < 4; ++j) {
+    int m = m0 + j;
+    bool pad = m >= a.M || node_is_pad(a.txt_mask, a.mask_kind, (int64_t)bb * a.txt_ms + m);
+    rx[j] = 1.f / fmaxf(sqrtf(a.nx2[(int64_t)bb * MP + m]), a.eps);
+    xg[j] = pad ? 1e4f : 0.f;
+    if (!pad && tr == 0) xcount += 1.f;
+  }
+  uint32_t ypad = 0;                                 // bit i: image row of pass i is padding
+  float ycount = 0.f;
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    int n = tr + i * RP;
+    bool pad = n >= a.N || node_is_pad(a.img_mask, a.mask_kind, (int64_t)bb * a.img_ms + n);
+    ypad |= (pad ? 1u : 0u) << i;
+    if (tc == 0 && !pad) ycount += 1.f;
+  }
+  auto row_inv_norm = [&](int i) {
+    int n = tr + i * RP;
+    float n2 = n < a.N ? a.ny2[(int64_t)bb * a.Nld + n] : 1.f;
+    return 1.f / fmaxf(sqrtf(n2), a.eps);
+  };
+  if (tid < SPC * 2) (&s_cnt[0][0])[tid] = 0.f;
+  __syncthreads();
+  xcount = warp_sum(xcount);
+  ycount = warp_sum(ycount);
+  if (lane == 0) { atomicAdd(&s_cnt[sub][0], xcount); atomicAdd(&s_cnt[sub][1], ycount); }
+  __syncthreads();
+  const float xlen = s_cnt[sub][0], ylen = s_cnt[sub][1];
+  float* Sg = a.S + (int64_t)bb * a.N * MP;
+  const bool empty = (xlen == 0.f || ylen == 0.f);   // model_ot.py:62: whole plan masked -> 0
+
+  // ---- kernel matrix A = exp(-C/beta), R = 1 on valid pairs ----------------------------------
+  float2 A[RPT][2], R[RPT][2];
+  float u[RPT];
   const float nib = -1.f / a.beta;
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
@@ -324,65 +379,93 @@ __global__ void __launch_bounds__(256) ot_ipot_kernel(IpotArgs a) {
     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < a.N) s4 = *reinterpret_cast<const float4*>(Sg + (int64_t)n * MP + m0);
     const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+    const float ryi = row_inv_norm(i);
+    float av[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      bool valid = yguard[i] == 0.f && xg[j] == 0.f;
-      float c = 1.f - sv[j] * rx[j] * ry[i];
-      A[i][j] = valid ? expf(c * nib) : 0.f;
-      T[i][j] = valid ? 1.f : 0.f;
+      bool valid = !((ypad >> i) & 1u) && xg[j] == 0.f && !empty;
+      av[j] = valid ? expf((1.f - sv[j] * rx[j] * ryi) * nib) : 0.f;
     }
+    A[i][0] = f2(av[0], av[1]); A[i][1] = f2(av[2], av[3]);
+    R[i][0] = f2(av[0] != 0.f ? 1.f : 0.f, av[1] != 0.f ? 1.f : 0.f);
+    R[i][1] = f2(av[2] != 0.f ? 1.f : 0.f, av[3] != 0.f ? 1.f : 0.f);
+    u[i] = 1.f;
   }
-  if (tid < MP) s_sigma[tid] = s_xguard[tid] == 0.f ? 1.f / xlen : 0.f;
-  __syncthreads();
+  // exp() can only return 0 for a valid pair if C/beta > 87, impossible for C <= 2, beta >= 0.03
+  float v[4], sig[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v[j] = 1.f; sig[j] = (xg[j] == 0.f && !empty) ? 1.f / xlen : 0.f; }
 
-  // ---- IPOT iterations (model_ot.py:55-61) -------------------------------------------------
-  float sig[4];
+  // ---- iterations ------------------------------------------------------------------------------
+  int flip = 0;
   for (int it = 0; it < a.iters; ++it) {
-    float delta[RPT];
 #pragma unroll
-    for (int i = 0; i < RPT; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) T[i][j] *= A[i][j];  // Q = A * T
+    for (int i = 0; i < RPT; ++i) {           // R1 = A * R
+      R[i][0] = __fmul2_rn(R[i][0], A[i][0]);
+      R[i][1] = __fmul2_rn(R[i][1], A[i][1]);
+    }
+    float z[RPT];
     for (int kk = 0; kk < a.k; ++kk) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) sig[j] = s_sigma[m0 + j];
-      float cs[4] = {0.f, 0.f, 0.f, 0.f};
+      const float2 w0 = f2(v[0] * sig[0], v[1] * sig[1]), w1 = f2(v[2] * sig[2], v[3] * sig[3]);
+      float2 cs0 = f2(0.f, 0.f), cs1 = f2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
-        float rs = T[i][0] * sig[0] + T[i][1] * sig[1] + T[i][2] * sig[2] + T[i][3] * sig[3];
+        float2 p = __ffma2_rn(R[i][1], w1, __fmul2_rn(R[i][0], w0));
+        float rs = p.x + p.y;
 #pragma unroll
         for (int o = 1; o < TC; o <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-        float d = 1.f / (ylen * rs + yguard[i]);
-        delta[i] = d;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cs[j] += d * T[i][j];
+        float d = 1.f / (ylen * (u[i] * rs) + (((ypad >> i) & 1u) ? 1e4f : 0.f));
+        z[i] = d * u[i];
+        const float2 zz = f2(z[i], z[i]);
+        cs0 = __ffma2_rn(zz, R[i][0], cs0);
+        cs1 = __ffma2_rn(zz, R[i][1], cs1);
       }
+      float cs[4] = {cs0.x, cs0.y, cs1.x, cs1.y};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
 #pragma unroll
         for (int o = TC; o < 32; o <<= 1) cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], o);
       }
-      __syncthreads();  // everyone has read s_sigma
-      if (lane < TC) *reinterpret_cast<float4*>(&s_red[w][m0]) = make_float4(cs[0], cs[1], cs[2], cs[3]);
-      __syncthreads();
-      if (tid < MP) {
-        float v = 0.f;
+      if constexpr (G > 32) {
+        if (lane < TC) *reinterpret_cast<float4*>(&s_red[flip][w][m0]) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+        __syncthreads();
+        float4 t4 = *reinterpret_cast<const float4*>(&s_red[flip][0][m0]);
 #pragma unroll
-        for (int ww = 0; ww < 8; ++ww) v += s_red[ww][tid];
-        s_sigma[tid] = 1.f / (xlen * v + s_xguard[tid]);
+        for (int ww = 1; ww < NW; ++ww) {
+          float4 q4 = *reinterpret_cast<const float4*>(&s_red[flip][ww][m0]);
+          t4.x += q4.x; t4.y += q4.y; t4.z += q4.z; t4.w += q4.w;
+        }
+        cs[0] = t4.x; cs[1] = t4.y; cs[2] = t4.z; cs[3] = t4.w;
+        flip ^= 1;
       }
-      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sig[j] = 1.f / (xlen * (v[j] * cs[j]) + xg[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sig[j] = s_sigma[m0 + j];
+    for (int i = 0; i < RPT; ++i) u[i] = z[i];
 #pragma unroll
-    for (int i = 0; i < RPT; ++i)
+    for (int j = 0; j < 4; ++j) v[j] *= sig[j];
+    if ((it % kRefold) == kRefold - 1) {     // fold the scalings back into R
+      const float2 v0 = f2(v[0], v[1]), v1 = f2(v[2], v[3]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) T[i][j] = delta[i] * T[i][j] * sig[j];
+      for (int i = 0; i < RPT; ++i) {
+        const float2 uu = f2(u[i], u[i]);
+        R[i][0] = __fmul2_rn(__fmul2_rn(R[i][0], uu), v0);
+        R[i][1] = __fmul2_rn(__fmul2_rn(R[i][1], uu), v1);
+        u[i] = 1.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = 1.f;   // sigma itself is unchanged by the fold
+    }
   }
-  (void)RW;
 
-  // ---- distance, W, normalisation-backward coefficients -----------------------------------
+  // ---- distance, W, normalisation-backward coefficients (T = u R v) --------------------------
+  // |y|^2 is re-read here (A is dead, registers are free) and must be read by every thread of a
+  // row before the row's tc == 0 thread overwrites it with ay.
+  float ryv[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) ryv[i] = row_inv_norm(i);
+  group_sync();
   float dsum = 0.f;
   float px[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -391,26 +474,28 @@ __global__ void __launch_bounds__(256) ot_ipot_kernel(IpotArgs a) {
     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < a.N) s4 = *reinterpret_cast<const float4*>(Sg + (int64_t)n * MP + m0);
     const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+    const float rr[4] = {R[i][0].x, R[i][0].y, R[i][1].x, R[i][1].y};
+    const float ryi = ryv[i];
     float py = 0.f, wv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      bool valid = yguard[i] == 0.f && xg[j] == 0.f;
-      float shat = sv[j] * rx[j] * ry[i];
-      float tt = valid ? T[i][j] : 0.f;  // model_ot.py:62 final mask (also drops NaNs at pads)
+      bool valid = !((ypad >> i) & 1u) && xg[j] == 0.f && !empty;
+      float shat = sv[j] * rx[j] * ryi;
+      float tt = valid ? u[i] * rr[j] * v[j] : 0.f;   // model_ot.py:62 final mask
       dsum += (1.f - shat) * tt;
       float tg = a.scale * tt;
       px[j] += tg * shat;
       py += tg * shat;
-      wv[j] = tg * rx[j] * ry[i];
+      wv[j] = tg * rx[j] * ryi;
     }
 #pragma unroll
     for (int o = 1; o < TC; o <<= 1) py += __shfl_xor_sync(0xffffffffu, py, o);
-    if (n < a.N) {
+    if (n < a.N && live) {
       *reinterpret_cast<float4*>(Sg + (int64_t)n * MP + m0) = make_float4(wv[0], wv[1], wv[2], wv[3]);
       if (tc == 0) {
         float n2 = a.ny2[(int64_t)b * a.Nld + n];
         // |y| < eps: F.normalize divides by eps and the projection term has no gradient
-        a.ny2[(int64_t)b * a.Nld + n] = (sqrtf(n2) >= a.eps) ? py * ry[i] * ry[i] : 0.f;
+        a.ny2[(int64_t)b * a.Nld + n] = (sqrtf(n2) >= a.eps) ? py * ryi * ryi : 0.f;
       }
     }
   }
@@ -420,23 +505,36 @@ __global__ void __launch_bounds__(256) ot_ipot_kernel(IpotArgs a) {
     for (int o = TC; o < 32; o <<= 1) px[j] += __shfl_xor_sync(0xffffffffu, px[j], o);
   }
   dsum = warp_sum(dsum);
-  __syncthreads();
-  if (lane < TC) *reinterpret_cast<float4*>(&s_red[w][m0]) = make_float4(px[0], px[1], px[2], px[3]);
-  if (lane == 0) s_red2[w] = dsum;
-  __syncthreads();
-  if (tid < MP) {
-    float v = 0.f;
+  if constexpr (G > 32) {
+    __syncthreads();
+    if (lane < TC) *reinterpret_cast<float4*>(&s_red[0][w][m0]) = make_float4(px[0], px[1], px[2], px[3]);
+    if (lane == 0) s_red2[w] = dsum;
+    __syncthreads();
+    if (tid < MP) {
+      float t = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) v += s_red[ww][tid];
-    float n2 = a.nx2[(int64_t)b * MP + tid];
-    float r = s_rx[tid];
-    a.nx2[(int64_t)b * MP + tid] = (sqrtf(n2) >= a.eps) ? v * r * r : 0.f;
-  }
-  if (tid == 0) {
-    float v = 0.f;
+      for (int ww = 0; ww < NW; ++ww) t += s_red[0][ww][tid];
+      float n2 = a.nx2[(int64_t)b * MP + tid];
+      float r = 1.f / fmaxf(sqrtf(n2), a.eps);
+      a.nx2[(int64_t)b * MP + tid] = (sqrtf(n2) >= a.eps) ? t * r * r : 0.f;
+    }
+    if (tid == 0) {
+      float t = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) v += s_red2[ww];
-    a.dist[b] = v;
+      for (int ww = 0; ww < NW; ++ww) t += s_red2[ww];
+      a.dist[b] = t;
+    }
+  } else {
+    if (live) {
+      if (tr == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float n2 = a.nx2[(int64_t)b * MP + m0 + j];
+          a.nx2[(int64_t)b * MP + m0 + j] = (sqrtf(n2) >= a.eps) ? px[j] * rx[j] * rx[j] : 0.f;
+        }
+      }
+      if (lane == 0) a.dist[b] = dsum;
+    }
   }
 }
 
@@ -555,6 +653,8 @@ __global__ void __launch_bounds__(256) ot_ipot_big_kernel(IpotBigArgs p) {
 
 // ------------------------------------------------------------------------------------------
 // Kernel C: dy = -W^t x + ay*y (rows of this CTA), dx = -W y + ax*x (partial over its rows).
+// Same cp.async ring as kernel A.  fp32: 3xTF32 on fp32 slabs.  bf16: bf16 mma; W is kept in
+// smem as bf16 in both orientations, the slabs' "across K" operands come through ldmatrix.trans.
 // ------------------------------------------------------------------------------------------
 template <int DT>
 __device__ __forceinline__ void store2(typename In<DT>::type* p, float v0, float v1) {
@@ -565,15 +665,33 @@ __device__ __forceinline__ void store2(typename In<DT>::type* p, float v0, float
   }
 }
 
+template <int DT>
+struct GradCfg {
+  static constexpr bool F32 = DT == CE_F32;
+  static constexpr int RS = kSlabBytes + (F32 ? 32 : 16);   // fp32: 40 words (== 8 mod 32); bf16: 36 words
+  static constexpr int DCOLS = kSlabBytes / (F32 ? 4 : 2);  // columns per slab: 32 / 64
+  // W storage: fp32 [rows][MP+4] floats, or bf16 [rows][MP+8] + [MP][rows+8]
+  __host__ __device__ static size_t w_bytes(int MP, int rows) {
+    return F32 ? sizeof(float) * (size_t)rows * (MP + 4)
+               : 2 * ((size_t)rows * (MP + 8) + (size_t)MP * (rows + 8));
+  }
+  __host__ __device__ static size_t smem_bytes(int MP, int rows) {
+    return (size_t)kStages * (MP + rows) * RS + w_bytes(MP, rows) + sizeof(float) * (MP + rows) + 64;
+  }
+};
+
 template <int DT, int MP, int NWARPS, int TPW>
 __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
-  constexpr int NSPLIT = (DT == CE_F32) ? 3 : 1;
+  using Cfg = GradCfg<DT>;
+  constexpr bool F32 = Cfg::F32;
   constexpr int NT = NWARPS * 32;
-  constexpr int LDW = MP + 4;
-  constexpr int NOUT = (MP / 16) * (kDC / 8);            // dx output tiles per step
-  constexpr int OPW = (NOUT + NWARPS - 1) / NWARPS;      // per warp
+  constexpr int RS = Cfg::RS, RSW = RS / 4;
+  constexpr int DC = Cfg::DCOLS;
+  constexpr int ESZ = F32 ? 4 : 2;
+  constexpr int NOUT = (MP / 16) * (DC / 8);             // dx output tiles per slab
+  constexpr int OPW = (NOUT + NWARPS - 1) / NWARPS;
   using T = typename In<DT>::type;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(16) uint8_t smem_g[];
   const int b = blockIdx.x, ns = blockIdx.y;
   const int ntiles = (a.N + 15) / 16;
   const int tile0 = ns * a.tiles_per_cta;
@@ -581,77 +699,126 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
   const int row0 = tile0 * 16;
   const int rows = my_tiles * 16;
   const int rows_valid = min(rows, a.N - row0);
-  float* xs = smem;                       // [MP][kLdB]
-  float* ys = xs + MP * kLdB;             // [rows][kLdB]
-  float* Ws = ys + rows * kLdB;           // [rows][LDW]
-  float* axs = Ws + rows * LDW;           // [MP]
-  float* ays = axs + MP;                  // [rows]
-  const T* xg = reinterpret_cast<const T*>(a.txt) + (int64_t)b * a.txt_bs;
-  const T* yg = reinterpret_cast<const T*>(a.img) + (int64_t)b * a.img_bs + (int64_t)row0 * a.D;
+  const int stage_bytes = (MP + rows) * RS;
+  const int row_bytes = a.D * ESZ;
+  uint8_t* wbase = smem_g + kStages * stage_bytes;
+  float* axs = reinterpret_cast<float*>(wbase + Cfg::w_bytes(MP, rows));
+  float* ays = axs + MP;
+  const uint8_t* xg = reinterpret_cast<const uint8_t*>(a.txt) + (int64_t)b * a.txt_bs * ESZ;
+  const uint8_t* yg = reinterpret_cast<const uint8_t*>(a.img) + ((int64_t)b * a.img_bs + (int64_t)row0 * a.D) * ESZ;
   T* dxg = reinterpret_cast<T*>(a.dtxt) + (int64_t)b * a.txt_bs;
   T* dyg = reinterpret_cast<T*>(a.dimg) + (int64_t)b * a.img_bs + (int64_t)row0 * a.D;
   const int w = warp_id(), lane = lane_id(), g = lane >> 2, t = lane & 3;
+  const int nslab = (row_bytes + kSlabBytes - 1) / kSlabBytes;
 
-  {  // W, ax, ay for this CTA's rows
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) {
+    if (s < nslab) issue_slab<RS>(smem_g + s * stage_bytes, xg, yg, MP, a.M, rows, rows_valid, row_bytes, s, NT);
+    cp_async_commit();
+  }
+
+  // W, ax, ay of this CTA's rows (overlaps the first slabs' flight)
+  constexpr int LDW = MP + 4;                 // fp32 W row stride (floats)
+  constexpr int LDWB = MP + 8;                // bf16 W[n][m] row stride (elements)
+  const int LDWT = rows + 8;                  // bf16 W^t[m][n] row stride (elements)
+  float* Ws = reinterpret_cast<float*>(wbase);
+  __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(wbase);
+  __nv_bfloat16* Wt = Wb + (size_t)rows * LDWB;
+  {
     const float* Wg = a.S + ((int64_t)b * a.N + row0) * MP;
     for (int idx = threadIdx.x; idx < rows * (MP / 4); idx += NT) {
       int r = idx / (MP / 4), c = (idx % (MP / 4)) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < rows_valid) v = *reinterpret_cast<const float4*>(Wg + (int64_t)r * MP + c);
-      *reinterpret_cast<float4*>(Ws + r * LDW + c) = v;
+      if constexpr (F32) {
+        *reinterpret_cast<float4*>(Ws + r * LDW + c) = v;
+      } else {
+        uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        *reinterpret_cast<uint2*>(Wb + r * LDWB + c) = pk;
+        Wt[(c + 0) * LDWT + r] = __float2bfloat16_rn(v.x);
+        Wt[(c + 1) * LDWT + r] = __float2bfloat16_rn(v.y);
+        Wt[(c + 2) * LDWT + r] = __float2bfloat16_rn(v.z);
+        Wt[(c + 3) * LDWT + r] = __float2bfloat16_rn(v.w);
+      }
     }
     for (int m = threadIdx.x; m < MP; m += NT) axs[m] = a.nx2[(int64_t)b * MP + m];
     for (int r = threadIdx.x; r < rows; r += NT)
       ays[r] = r < rows_valid ? a.ny2[(int64_t)b * a.Nld + row0 + r] : 0.f;
   }
 
-  for (int d0 = 0; d0 < a.D; d0 += kDC) {
+  for (int c = 0; c < nslab; ++c) {
+    {
+      const int cn = c + kStages - 1;
+      if (cn < nslab) issue_slab<RS>(smem_g + (cn % kStages) * stage_bytes, xg, yg, MP, a.M, rows, rows_valid, row_bytes, cn, NT);
+      cp_async_commit();
+    }
+    cp_async_wait<kStages - 1>();
     __syncthreads();
-    stage_rows<DT, kLdB>(xs, xg, MP, a.M, a.D, d0, NT);
-    stage_rows<DT, kLdB>(ys, yg, rows, rows_valid, a.D, d0, NT);
-    __syncthreads();
+    const uint8_t* stage = smem_g + (c % kStages) * stage_bytes;
+    const uint32_t* xs = reinterpret_cast<const uint32_t*>(stage);
+    const uint32_t* ys = xs + MP * RSW;
+    const int d0 = c * DC;
 
     // ---- dy tiles: rows of this warp, K = text nodes -------------------------------------
 #pragma unroll
     for (int i = 0; i < TPW; ++i) {
       int tile = w + i * NWARPS;
       if (tile < my_tiles) {
-        float acc[kDC / 8][4];
+        float acc[DC / 8][4];
 #pragma unroll
-        for (int j = 0; j < kDC / 8; ++j)
+        for (int j = 0; j < DC / 8; ++j)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+          for (int cc = 0; cc < 4; ++cc) acc[j][cc] = 0.f;
+        if constexpr (F32) {
 #pragma unroll
-        for (int ks = 0; ks < MP / 8; ++ks) {
-          const float* wr = Ws + (tile * 16 + g) * LDW + ks * 8 + t;
-          uint32_t ahi[4], alo[4];
-          split_tf32<NSPLIT>(wr[0], ahi[0], alo[0]);
-          split_tf32<NSPLIT>(wr[8 * LDW], ahi[1], alo[1]);
-          split_tf32<NSPLIT>(wr[4], ahi[2], alo[2]);
-          split_tf32<NSPLIT>(wr[8 * LDW + 4], ahi[3], alo[3]);
+          for (int ks = 0; ks < MP / 8; ++ks) {
+            const float* wr = Ws + (tile * 16 + g) * LDW + ks * 8 + t;
+            uint32_t ahi[4], alo[4];
+            split_tf32<3>(wr[0], ahi[0], alo[0]);
+            split_tf32<3>(wr[8 * LDW], ahi[1], alo[1]);
+            split_tf32<3>(wr[4], ahi[2], alo[2]);
+            split_tf32<3>(wr[8 * LDW + 4], ahi[3], alo[3]);
 #pragma unroll
-          for (int j = 0; j < kDC / 8; ++j) {
-            uint32_t bhi[2], blo[2];
-            split_tf32<NSPLIT>(xs[(ks * 8 + t) * kLdB + 8 * j + g], bhi[0], blo[0]);
-            split_tf32<NSPLIT>(xs[(ks * 8 + t + 4) * kLdB + 8 * j + g], bhi[1], blo[1]);
-            mma_split<NSPLIT>(acc[j], ahi, alo, bhi, blo);
+            for (int j = 0; j < DC / 8; ++j) {
+              uint32_t bhi[2], blo[2];
+              split_tf32<3>(__uint_as_float(xs[(ks * 8 + t) * RSW + 8 * j + g]), bhi[0], blo[0]);
+              split_tf32<3>(__uint_as_float(xs[(ks * 8 + t + 4) * RSW + 8 * j + g]), bhi[1], blo[1]);
+              mma_split<3>(acc[j], ahi, alo, bhi, blo);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < MP / 16; ++ks) {
+            const uint32_t* wr = reinterpret_cast<const uint32_t*>(Wb + (tile * 16 + g) * LDWB + ks * 16) + t;
+            uint32_t af[4] = {wr[0], wr[8 * (LDWB / 2)], wr[4], wr[8 * (LDWB / 2) + 4]};
+#pragma unroll
+            for (int j = 0; j < DC / 8; ++j) {
+              uint32_t bf[2];
+              ldsm_x2_trans(bf, stage + (ks * 16 + (lane & 15)) * RS + j * 16);
+              mma_bf16(acc[j], af, bf);
+            }
           }
         }
         int r = tile * 16 + g;
 #pragma unroll
-        for (int j = 0; j < kDC / 8; ++j) {
+        for (int j = 0; j < DC / 8; ++j) {
           int d = 8 * j + 2 * t;
           if (d0 + d < a.D) {
+            float y00, y01, y10, y11;
+            if constexpr (F32) {
+              y00 = __uint_as_float(ys[r * RSW + d]); y01 = __uint_as_float(ys[r * RSW + d + 1]);
+              y10 = __uint_as_float(ys[(r + 8) * RSW + d]); y11 = __uint_as_float(ys[(r + 8) * RSW + d + 1]);
+            } else {
+              uint32_t u0 = ys[r * RSW + d / 2], u1 = ys[(r + 8) * RSW + d / 2];
+              y00 = bf_lo(u0); y01 = bf_hi(u0); y10 = bf_lo(u1); y11 = bf_hi(u1);
+            }
             if (r < rows_valid) {
               float ay = ays[r];
-              store2<DT>(dyg + (int64_t)r * a.D + d0 + d, ay * ys[r * kLdB + d] - acc[j][0],
-                         ay * ys[r * kLdB + d + 1] - acc[j][1]);
+              store2<DT>(dyg + (int64_t)r * a.D + d0 + d, ay * y00 - acc[j][0], ay * y01 - acc[j][1]);
             }
             if (r + 8 < rows_valid) {
               float ay = ays[r + 8];
-              store2<DT>(dyg + (int64_t)(r + 8) * a.D + d0 + d,
-                         ay * ys[(r + 8) * kLdB + d] - acc[j][2],
-                         ay * ys[(r + 8) * kLdB + d + 1] - acc[j][3]);
+              store2<DT>(dyg + (int64_t)(r + 8) * a.D + d0 + d, ay * y10 - acc[j][2], ay * y11 - acc[j][3]);
             }
           }
         }
@@ -663,30 +830,45 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
     for (int o = 0; o < OPW; ++o) {
       int ot = w + o * NWARPS;
       if (ot < NOUT) {
-        int mi = ot / (kDC / 8), j = ot % (kDC / 8);
+        int mi = ot / (DC / 8), j = ot % (DC / 8);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int ks = 0; ks < rows / 8; ++ks) {
-          const float* wr = Ws + (ks * 8 + t) * LDW + 16 * mi + g;
-          uint32_t ahi[4], alo[4];
-          split_tf32<NSPLIT>(wr[0], ahi[0], alo[0]);
-          split_tf32<NSPLIT>(wr[8], ahi[1], alo[1]);
-          split_tf32<NSPLIT>(wr[4 * LDW], ahi[2], alo[2]);
-          split_tf32<NSPLIT>(wr[4 * LDW + 8], ahi[3], alo[3]);
-          uint32_t bhi[2], blo[2];
-          split_tf32<NSPLIT>(ys[(ks * 8 + t) * kLdB + 8 * j + g], bhi[0], blo[0]);
-          split_tf32<NSPLIT>(ys[(ks * 8 + t + 4) * kLdB + 8 * j + g], bhi[1], blo[1]);
-          mma_split<NSPLIT>(acc, ahi, alo, bhi, blo);
+        if constexpr (F32) {
+          for (int ks = 0; ks < rows / 8; ++ks) {
+            const float* wr = Ws + (ks * 8 + t) * LDW + 16 * mi + g;
+            uint32_t ahi[4], alo[4];
+            split_tf32<3>(wr[0], ahi[0], alo[0]);
+            split_tf32<3>(wr[8], ahi[1], alo[1]);
+            split_tf32<3>(wr[4 * LDW], ahi[2], alo[2]);
+            split_tf32<3>(wr[4 * LDW + 8], ahi[3], alo[3]);
+            uint32_t bhi[2], blo[2];
+            split_tf32<3>(__uint_as_float(ys[(ks * 8 + t) * RSW + 8 * j + g]), bhi[0], blo[0]);
+            split_tf32<3>(__uint_as_float(ys[(ks * 8 + t + 4) * RSW + 8 * j + g]), bhi[1], blo[1]);
+            mma_split<3>(acc, ahi, alo, bhi, blo);
+          }
+        } else {
+          const uint8_t* ysb = stage + MP * RS;
+          for (int ks = 0; ks < rows / 16; ++ks) {
+            const uint32_t* wr = reinterpret_cast<const uint32_t*>(Wt + (16 * mi + g) * LDWT + ks * 16) + t;
+            uint32_t af[4] = {wr[0], wr[8 * (LDWT / 2)], wr[4], wr[8 * (LDWT / 2) + 4]};
+            uint32_t bf[2];
+            ldsm_x2_trans(bf, ysb + (ks * 16 + (lane & 15)) * RS + j * 16);
+            mma_bf16(acc, af, bf);
+          }
         }
         int m = 16 * mi + g, d = 8 * j + 2 * t;
         if (d0 + d < a.D) {
+          float x00, x01, x10, x11;
+          if constexpr (F32) {
+            x00 = __uint_as_float(xs[m * RSW + d]); x01 = __uint_as_float(xs[m * RSW + d + 1]);
+            x10 = __uint_as_float(xs[(m + 8) * RSW + d]); x11 = __uint_as_float(xs[(m + 8) * RSW + d + 1]);
+          } else {
+            uint32_t u0 = xs[m * RSW + d / 2], u1 = xs[(m + 8) * RSW + d / 2];
+            x00 = bf_lo(u0); x01 = bf_hi(u0); x10 = bf_lo(u1); x11 = bf_hi(u1);
+          }
           if (a.nsplit == 1) {
-            if (m < a.M)
-              store2<DT>(dxg + (int64_t)m * a.D + d0 + d, axs[m] * xs[m * kLdB + d] - acc[0],
-                         axs[m] * xs[m * kLdB + d + 1] - acc[1]);
+            if (m < a.M) store2<DT>(dxg + (int64_t)m * a.D + d0 + d, axs[m] * x00 - acc[0], axs[m] * x01 - acc[1]);
             if (m + 8 < a.M)
-              store2<DT>(dxg + (int64_t)(m + 8) * a.D + d0 + d,
-                         axs[m + 8] * xs[(m + 8) * kLdB + d] - acc[2],
-                         axs[m + 8] * xs[(m + 8) * kLdB + d + 1] - acc[3]);
+              store2<DT>(dxg + (int64_t)(m + 8) * a.D + d0 + d, axs[m + 8] * x10 - acc[2], axs[m + 8] * x11 - acc[3]);
           } else {
             float* dacc = a.dx_acc + ((int64_t)b * a.M) * a.D + d0 + d;
             if (m < a.M) {
@@ -701,6 +883,7 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
         }
       }
     }
+    __syncthreads();
   }
 }
 
@@ -856,8 +1039,7 @@ __global__ void scale_inplace_kernel(void* x, int64_t rows, int64_t row_len, int
 // host dispatch
 // ------------------------------------------------------------------------------------------
 struct OtPlan {
-  int MP, nwarps, tpw, tiles_per_cta, nsplit, rpt;
-  size_t smem_cost, smem_grad;
+  int MP, nwarps, tpw, tiles_per_cta, nsplit, rpt, rows;
 };
 
 int make_plan(int M, int N, OtPlan* p) {
@@ -871,9 +1053,7 @@ int make_plan(int M, int N, OtPlan* p) {
   p->nsplit = (ntiles + cap - 1) / cap;
   p->tiles_per_cta = (ntiles + p->nsplit - 1) / p->nsplit;
   int rows = p->tiles_per_cta * 16;
-  p->smem_cost = sizeof(float) * ((size_t)p->MP * kLdA + (size_t)rows * kLdA);
-  p->smem_grad = sizeof(float) * ((size_t)p->MP * kLdB + (size_t)rows * kLdB +
-                                  (size_t)rows * (p->MP + 4) + p->MP + rows);
+  p->rows = rows;
   int rp = 256 / (p->MP / 4);
   p->rpt = (N + rp - 1) / rp;
   return CE_OK;
@@ -883,13 +1063,16 @@ template <int DT, int MP, int NW, int TPW>
 int launch_cost_grad(bool grad, const OtArgs& a, const OtPlan& p, cudaStream_t st) {
   dim3 grid(a.B, p.nsplit);
   if (!grad) {
+    const size_t smem = (size_t)kStages * (MP + p.rows) * kRsA;
     auto kern = ot_cost_kernel<DT, MP, NW, TPW>;
-    CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_cost));
-    kern<<<grid, NW * 32, p.smem_cost, st>>>(a);
+    CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NW * 32, smem, st>>>(a);
   } else {
+    const size_t smem = GradCfg<DT>::smem_bytes(MP, p.rows);
+    if (smem > 227 * 1024) return fail(CE_ERR_SHAPE, "OT: gradient kernel needs %zu B of shared memory", smem);
     auto kern = ot_grad_kernel<DT, MP, NW, TPW>;
-    CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_grad));
-    kern<<<grid, NW * 32, p.smem_grad, st>>>(a);
+    CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NW * 32, smem, st>>>(a);
   }
   CE_LAUNCH_CHECK();
   return CE_OK;
@@ -911,12 +1094,19 @@ int dispatch_mp(bool grad, const OtArgs& a, const OtPlan& p, cudaStream_t st) {
 }
 
 template <int MP>
-int launch_ipot_mp(const IpotArgs& a, int rpt, cudaStream_t st, bool* handled) {
+int launch_ipot_mp(const IpotArgs& a, int N, cudaStream_t st, bool* handled) {
   *handled = true;
-#define CE_IPOT_CASE(R) \
-  if (rpt <= R) { ot_ipot_kernel<MP, R><<<a.B, 256, 0, st>>>(a); return CE_OK; }
-  CE_IPOT_CASE(1) CE_IPOT_CASE(2) CE_IPOT_CASE(4) CE_IPOT_CASE(7) CE_IPOT_CASE(9)
-  CE_IPOT_CASE(13) CE_IPOT_CASE(19)
+  // one warp per sample while the plan fits ~40 registers per lane, else 256 or 512 threads
+  constexpr int TC = MP / 4;
+  const int rptw = (N + 32 / TC - 1) / (32 / TC);
+  const int rpt256 = (N + 256 / TC - 1) / (256 / TC);
+  const int rpt512 = (N + 512 / TC - 1) / (512 / TC);
+#define CE_IPOT_CASE(COND, R, G) \
+  if (COND <= R) { ot_ipot_kernel<MP, R, G><<<(G == 32 ? (a.B + 7) / 8 : a.B), (G < 256 ? 256 : G), 0, st>>>(a); return CE_OK; }
+  CE_IPOT_CASE(rptw, 2, 32) CE_IPOT_CASE(rptw, 4, 32) CE_IPOT_CASE(rptw, 7, 32) CE_IPOT_CASE(rptw, 10, 32)
+  CE_IPOT_CASE(rpt256, 1, 256) CE_IPOT_CASE(rpt256, 2, 256) CE_IPOT_CASE(rpt256, 4, 256)
+  CE_IPOT_CASE(rpt512, 3, 512) CE_IPOT_CASE(rpt512, 5, 512) CE_IPOT_CASE(rpt512, 7, 512)
+  CE_IPOT_CASE(rpt512, 10, 512) CE_IPOT_CASE(rpt512, 13, 512)
 #undef CE_IPOT_CASE
   *handled = false;
   return CE_OK;
@@ -991,9 +1181,9 @@ extern "C" int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* i
   ia.iters = iters; ia.k = k; ia.dist = dist;
   bool handled = false;
   switch (p.MP) {
-    case 16: CE_TRY(launch_ipot_mp<16>(ia, p.rpt, st, &handled)); break;
-    case 32: CE_TRY(launch_ipot_mp<32>(ia, p.rpt, st, &handled)); break;
-    default: CE_TRY(launch_ipot_mp<64>(ia, p.rpt, st, &handled)); break;
+    case 16: CE_TRY(launch_ipot_mp<16>(ia, N, st, &handled)); break;
+    case 32: CE_TRY(launch_ipot_mp<32>(ia, N, st, &handled)); break;
+    default: CE_TRY(launch_ipot_mp<64>(ia, N, st, &handled)); break;
   }
   if (!handled) {
     IpotBigArgs ba{ia, scratch, p.MP};
