@@ -10,6 +10,8 @@
 // (d x^ = -dC y^,  dx = (dx^ - x^ (x^.dx^)) / |x|,  x^.dx^ = -sum_n dC[m,n] S^[m,n]).
 // The contractions run on the tensor cores through warp-level mma (tf32, 3-way split in fp32
 // mode so the cost matrix keeps fp32 accuracy: IPOT amplifies cost error by iters/beta).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "ce_common.cuh"
@@ -83,7 +85,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int kSlabBytes = 128;   // bytes of one row staged per step (32 fp32 / 64 bf16 columns)
-constexpr int kStages = 3;
+constexpr int kStages = 2;
 
 // Stage slab `c` of the MP text rows followed by `rows` image rows; RS = smem row stride in bytes.
 template <int RS>
@@ -307,20 +309,29 @@ __device__ __forceinline__ bool node_is_pad(const void* mask, int kind, int64_t 
 constexpr int kRefold = 4;
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+// 1/x in one MUFU (<= 1 ulp); the full-precision division's slow path doubled the loop's length
+__device__ __forceinline__ float frcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // One launch geometry for both solvers:
 //   G    threads cooperating on one sample (32: one warp, no block barrier; 256: one CTA)
 //   TC   = MP/4 threads across a row, each owning 4 consecutive text nodes (two float2)
 //   RP   = G/TC image rows per pass, RPT passes
-template <int MP, int RPT, int G>
-__global__ void __launch_bounds__((G < 256 ? 256 : G)) ot_ipot_kernel(IpotArgs a) {
+// SCHEME 0: every thread sums the warps' column partials itself (1 barrier / iteration)
+// SCHEME 1: warp 0 sums them and publishes sigma (2 barriers / iteration, fewer instructions)
+template <int MP, int RPT, int G, int MINB = 1, int SCHEME = 0>
+__global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(IpotArgs a) {
   constexpr int TC = MP / 4;
   constexpr int RP = G / TC;
   constexpr int BT = G < 256 ? 256 : G;   // threads per CTA
   constexpr int SPC = BT / G;             // samples per CTA
   constexpr int NW = G / 32;          // warps per sample
   static_assert(TC <= 32 && RP >= 1, "layout");
-  __shared__ __align__(16) float s_red[2][NW][MP];   // column partials (G == 256 only)
+  __shared__ __align__(16) float s_red[2][NW][MP];   // column partials (G > 32 only)
+  __shared__ __align__(16) float s_sig[2][MP];
   __shared__ float s_cnt[SPC][2];
   __shared__ float s_red2[NW];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -372,6 +383,15 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G)) ot_ipot_kernel(IpotArgs a
   // ---- kernel matrix A = exp(-C/beta), R = 1 on valid pairs ----------------------------------
   float2 A[RPT][2], R[RPT][2];
   float u[RPT];
+  constexpr int NG = (RPT + TC - 1) / TC;   // groups of TC rows; lane tc owns row gi*TC + tc of group gi
+  float uown[NG], ygown[NG], zown[NG];
+#pragma unroll
+  for (int gi = 0; gi < NG; ++gi) {
+    uown[gi] = 1.f;
+    zown[gi] = 1.f;
+    const int i = gi * TC + tc;
+    ygown[gi] = (i >= RPT || ((ypad >> i) & 1u)) ? 1e4f : 0.f;
+  }
   const float nib = -1.f / a.beta;
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
@@ -408,17 +428,49 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G)) ot_ipot_kernel(IpotArgs a
     for (int kk = 0; kk < a.k; ++kk) {
       const float2 w0 = f2(v[0] * sig[0], v[1] * sig[1]), w1 = f2(v[2] * sig[2], v[3] * sig[3]);
       float2 cs0 = f2(0.f, 0.f), cs1 = f2(0.f, 0.f);
+      float rsv[RPT];
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
         float2 p = __ffma2_rn(R[i][1], w1, __fmul2_rn(R[i][0], w0));
-        float rs = p.x + p.y;
+        rsv[i] = p.x + p.y;
+      }
+      // Row sums over the TC lanes of a row.  Rows are taken TC at a time: a butterfly that halves
+      // the number of live values per step leaves lane tc with the full sum of row (i0 + tc) for
+      // TC-1 shuffles per TC rows (instead of TC*log2(TC)); that lane alone computes delta, which is
+      // then handed back to the row's lanes with one shuffle per row.
 #pragma unroll
-        for (int o = 1; o < TC; o <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-        float d = 1.f / (ylen * (u[i] * rs) + (((ypad >> i) & 1u) ? 1e4f : 0.f));
-        z[i] = d * u[i];
-        const float2 zz = f2(z[i], z[i]);
-        cs0 = __ffma2_rn(zz, R[i][0], cs0);
-        cs1 = __ffma2_rn(zz, R[i][1], cs1);
+      for (int gi = 0; gi < NG; ++gi) {
+        constexpr int kNone = 0;
+        (void)kNone;
+        const int i0 = gi * TC;
+        float vals[TC];
+#pragma unroll
+        for (int q = 0; q < TC; ++q) vals[q] = (i0 + q < RPT) ? rsv[(i0 + q < RPT) ? i0 + q : 0] : 0.f;
+#pragma unroll
+        for (int half = TC / 2; half >= 1; half >>= 1) {
+          const bool upper = (tc & half) != 0;
+#pragma unroll
+          for (int q = 0; q < half; ++q) {
+            float keep = upper ? vals[q + half] : vals[q];
+            float send = upper ? vals[q] : vals[q + half];
+            vals[q] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+          }
+        }
+        // lane tc now holds the full sum of row i0 + tc; it alone computes that row's delta
+        const float uo = uown[gi];
+        const float d = frcp(ylen * (uo * vals[0]) + ygown[gi]);
+        const float zo = d * uo;
+        zown[gi] = zo;
+#pragma unroll
+        for (int q = 0; q < TC; ++q) {
+          if (i0 + q < RPT) {
+            float zq = __shfl_sync(0xffffffffu, zo, (lane & ~(TC - 1)) | q);
+            z[(i0 + q < RPT) ? i0 + q : 0] = zq;
+            const float2 zz = f2(zq, zq);
+            cs0 = __ffma2_rn(zz, R[(i0 + q < RPT) ? i0 + q : 0][0], cs0);
+            cs1 = __ffma2_rn(zz, R[(i0 + q < RPT) ? i0 + q : 0][1], cs1);
+          }
+        }
       }
       float cs[4] = {cs0.x, cs0.y, cs1.x, cs1.y};
 #pragma unroll
@@ -426,23 +478,42 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G)) ot_ipot_kernel(IpotArgs a
 #pragma unroll
         for (int o = TC; o < 32; o <<= 1) cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], o);
       }
-      if constexpr (G > 32) {
+      if constexpr (G > 32 && SCHEME == 0) {
         if (lane < TC) *reinterpret_cast<float4*>(&s_red[flip][w][m0]) = make_float4(cs[0], cs[1], cs[2], cs[3]);
         __syncthreads();
         float4 t4 = *reinterpret_cast<const float4*>(&s_red[flip][0][m0]);
+        float2 ta = f2(t4.x, t4.y), tb = f2(t4.z, t4.w);
 #pragma unroll
         for (int ww = 1; ww < NW; ++ww) {
           float4 q4 = *reinterpret_cast<const float4*>(&s_red[flip][ww][m0]);
-          t4.x += q4.x; t4.y += q4.y; t4.z += q4.z; t4.w += q4.w;
+          ta = __fadd2_rn(ta, f2(q4.x, q4.y));
+          tb = __fadd2_rn(tb, f2(q4.z, q4.w));
         }
+        cs[0] = ta.x; cs[1] = ta.y; cs[2] = tb.x; cs[3] = tb.y;
+        flip ^= 1;
+      }
+      if constexpr (G > 32 && SCHEME == 1) {
+        // v is identical in every thread of a column group, so warp 0 can finish sigma alone
+        if (lane < TC) *reinterpret_cast<float4*>(&s_red[flip][w][m0]) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+        __syncthreads();
+        if (gt < MP) {
+          float tsum = 0.f;
+#pragma unroll
+          for (int ww = 0; ww < NW; ++ww) tsum += s_red[flip][ww][gt];
+          s_sig[flip][gt] = tsum;
+        }
+        __syncthreads();
+        float4 t4 = *reinterpret_cast<const float4*>(&s_sig[flip][m0]);
         cs[0] = t4.x; cs[1] = t4.y; cs[2] = t4.z; cs[3] = t4.w;
         flip ^= 1;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) sig[j] = 1.f / (xlen * (v[j] * cs[j]) + xg[j]);
+      for (int j = 0; j < 4; ++j) sig[j] = frcp(xlen * (v[j] * cs[j]) + xg[j]);
     }
 #pragma unroll
     for (int i = 0; i < RPT; ++i) u[i] = z[i];
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) uown[gi] = zown[gi];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] *= sig[j];
     if ((it % kRefold) == kRefold - 1) {     // fold the scalings back into R
@@ -454,6 +525,8 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G)) ot_ipot_kernel(IpotArgs a
         R[i][1] = __fmul2_rn(__fmul2_rn(R[i][1], uu), v1);
         u[i] = 1.f;
       }
+#pragma unroll
+      for (int gi = 0; gi < NG; ++gi) uown[gi] = 1.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = 1.f;   // sigma itself is unchanged by the fold
     }
@@ -1101,11 +1174,17 @@ int launch_ipot_mp(const IpotArgs& a, int N, cudaStream_t st, bool* handled) {
   const int rptw = (N + 32 / TC - 1) / (32 / TC);
   const int rpt256 = (N + 256 / TC - 1) / (256 / TC);
   const int rpt512 = (N + 512 / TC - 1) / (512 / TC);
-#define CE_IPOT_CASE(COND, R, G) \
-  if (COND <= R) { ot_ipot_kernel<MP, R, G><<<(G == 32 ? (a.B + 7) / 8 : a.B), (G < 256 ? 256 : G), 0, st>>>(a); return CE_OK; }
+  static const int variant = getenv("CE_IPOT_VARIANT") ? atoi(getenv("CE_IPOT_VARIANT")) : 0;  // tuning aid
+#define CE_IPOT_CASE(COND, R, G, ...) \
+  if (COND <= R) { ot_ipot_kernel<MP, R, G, ##__VA_ARGS__><<<(G == 32 ? (a.B + 7) / 8 : a.B), (G < 256 ? 256 : G), 0, st>>>(a); return CE_OK; }
   CE_IPOT_CASE(rptw, 2, 32) CE_IPOT_CASE(rptw, 4, 32) CE_IPOT_CASE(rptw, 7, 32) CE_IPOT_CASE(rptw, 10, 32)
   CE_IPOT_CASE(rpt256, 1, 256) CE_IPOT_CASE(rpt256, 2, 256) CE_IPOT_CASE(rpt256, 4, 256)
-  CE_IPOT_CASE(rpt512, 3, 512) CE_IPOT_CASE(rpt512, 5, 512) CE_IPOT_CASE(rpt512, 7, 512)
+  if (MP == 32 && variant == 1) { CE_IPOT_CASE(rpt256, 9, 256, 2, 0) }
+  if (MP == 32 && variant == 2) { CE_IPOT_CASE(rpt512, 5, 512, 1, 0) }
+  if (MP == 32 && variant == 3) { CE_IPOT_CASE(rpt256, 9, 256, 2, 1) }
+  if (MP == 32 && variant == 4) { CE_IPOT_CASE(rpt256, 9, 256, 1, 1) }
+  if (MP == 32 && variant == 5) { CE_IPOT_CASE(rpt512, 5, 512, 1, 1) }
+  CE_IPOT_CASE(rpt256, 7, 256) CE_IPOT_CASE(rpt256, 9, 256) CE_IPOT_CASE(rpt256, 13, 256)
   CE_IPOT_CASE(rpt512, 10, 512) CE_IPOT_CASE(rpt512, 13, 512)
 #undef CE_IPOT_CASE
   *handled = false;

@@ -1,0 +1,36 @@
+"""Times ce_ot_fwd_bwd (forward only = cost + IPOT, and full) for a workload; run once per
+CE_IPOT_VARIANT in a fresh process:  CE_IPOT_VARIANT=3 python tools/ot_tune.py c4 bf16"""
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from clip_event_b200 import functional as F_, synthetic as syn
+wl, dt = sys.argv[1], (torch.bfloat16 if sys.argv[2] == "bf16" else torch.float32)
+w = syn.WORKLOADS[wl]
+B = w.B if len(sys.argv) < 4 else int(sys.argv[3])
+etxt, obj, tnum, onum = syn.ot_inputs(B, w.M, w.N, w.D, 0, "ragged", dtype=dt)
+etxt, obj, tnum, onum = etxt.cuda(), obj.cuda(), tnum.cuda(), onum.cuda()
+def fwd():
+    with torch.no_grad():
+        return F_.ot_alignment(etxt, obj, tnum, onum)
+eg, og = etxt.clone().requires_grad_(True), obj.clone().requires_grad_(True)
+def full():
+    eg.grad = None; og.grad = None
+    l, _ = F_.ot_alignment(eg, og, tnum, onum)
+    l.backward()
+def time_it(fn, n=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s): fn()
+    torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
+    with torch.cuda.graph(g): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+l, d = fwd()
+print("variant=%s %s %s B=%d: fwd(cost+ipot) %.1f us   full %.1f us   loss %.6f" % (
+    os.environ.get("CE_IPOT_VARIANT", "0"), wl, sys.argv[2], B, time_it(fwd), time_it(full), l.item()))
