@@ -32,41 +32,58 @@ struct EpiStats {
     const float* rinv_row;
     const float* rinv_col;
     const float* logit_scale;
-    float2* part;  // [M, num_n_blk]  (max2, sum2) of the base-2 scaled logits
+    float2* part;  // [M, 2*num_n_blk]  (max2, sum2) of the base-2 scaled logits, per column half
     int M, N, num_n_blk;
     const int* lab;     // [M] column of the row's positive (or -1)
     float* lab_logit;   // [M] natural-log logit at that column, taken from the SAME accumulator so
                         //     that the tensor-core rounding cancels in (LSE - positive logit)
   };
   Params p;
-  float rs, m2, l;
+  float kk, rinv_r, m2, l;
   int lab;
-  __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et) {
-    for (int c = et; c < BN; c += 128) {
+  bool fixed_ref;
+  __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et2) {
+    for (int c = et2; c < BN; c += kEpiThreads) {
       int col = n_blk * BN + c;
       s_epi[c] = col < p.N ? __ldg(p.rinv_col + col) : 0.f;
     }
   }
   __device__ __forceinline__ void row_begin(int row, bool ok) {
-    rs = ok ? expf(__ldg(p.logit_scale)) * kLog2e * __ldg(p.rinv_row + row) : 0.f;
-    m2 = -INFINITY;
+    kk = expf(__ldg(p.logit_scale)) * kLog2e;          // base-2 temperature
+    rinv_r = ok ? __ldg(p.rinv_row + row) : 0.f;
+    // |cos| <= 1 bounds every scaled logit by kk: with a fixed reference the online max and its
+    // rescaling disappear.  2^(-2 kk) must stay a normal float, so only for kk <= 40 (s <= 27.7).
+    fixed_ref = kk <= 40.f;
+    m2 = fixed_ref ? kk : -INFINITY;
     l = 0.f;
     lab = ok ? __ldg(p.lab + row) : -1;
   }
   __device__ __forceinline__ void chunk(const float* acc, int col0, int lcol0, const float* s_epi,
                                         int row, bool) {
+    const float ks = kk * rinv_r;
+    const bool full = col0 + 32 <= p.N;
+    if ((unsigned)(lab - col0) < 32u) {
+      float pick = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pick = (col0 + i == lab) ? acc[i] * (ks * s_epi[lcol0 + i]) : pick;
+      p.lab_logit[row] = pick * kLn2;
+    }
+    if (fixed_ref && full) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        s0 += ex2(fmaf(acc[i], ks * s_epi[lcol0 + i], -kk));
+        s1 += ex2(fmaf(acc[i + 1], ks * s_epi[lcol0 + i + 1], -kk));
+      }
+      l += s0 + s1;
+      return;
+    }
     float v[32];
     float cm = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      v[i] = (col0 + i < p.N) ? acc[i] * rs * s_epi[lcol0 + i] : -INFINITY;
+      v[i] = (col0 + i < p.N) ? acc[i] * (ks * s_epi[lcol0 + i]) : -INFINITY;
       cm = fmaxf(cm, v[i]);
-    }
-    if ((unsigned)(lab - col0) < 32u) {
-      float pick = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) pick = (col0 + i == lab) ? v[i] : pick;
-      p.lab_logit[row] = pick * kLn2;
     }
     if (cm == -INFINITY) return;
     float mn = fmaxf(m2, cm);
@@ -76,8 +93,8 @@ struct EpiStats {
     l = l * ex2(m2 - mn) + s;
     m2 = mn;
   }
-  __device__ __forceinline__ void row_end(int row, bool ok, int, int n_blk, int, float*, int) {
-    if (ok) p.part[(int64_t)row * p.num_n_blk + n_blk] = make_float2(m2, l);
+  __device__ __forceinline__ void row_end(int row, bool ok, int, int n_blk, int, float*, int, int half) {
+    if (ok) p.part[(int64_t)row * (2 * p.num_n_blk) + 2 * n_blk + half] = make_float2(m2, l);
   }
 };
 
@@ -98,28 +115,33 @@ struct EpiGrad {
     void* G0;                // bf16 [M, ldg]  or tf32-hi fp32 [M, ldg]
     void* G1;                // tf32-lo
     int64_t ldg;
-    float* dls_part;         // [items, 4]
+    float* dls_part;         // [tiles, 8]
     int M, N, num_tiles;
   };
   Params p;
-  float rs, rinv_r, lse2r, ci, ct, dls;
+  float sl, rinv_r, lse2r, ci, ct, dls;
   int lab;
-  __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et) {
-    for (int c = et; c < BN; c += 128) {
+  // s_epi layout: [0,BN) rinv_col, [BN,2BN) col_lse2, [2BN,3BN) col_lab (int bits),
+  //               [3BN, 3BN+BN/32) bitmask of positive columns per 32-column chunk
+  __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et2) {
+    for (int c = et2; c < BN; c += kEpiThreads) {
       int col = n_blk * BN + c;
       bool ok = col < p.N;
+      int cl = ok ? __ldg(p.col_lab + col) : -1;
       s_epi[c] = ok ? __ldg(p.rinv_col + col) : 0.f;
       s_epi[BN + c] = ok ? __ldg(p.col_lse2 + col) : INFINITY;
-      s_epi[2 * BN + c] = __int_as_float(ok ? __ldg(p.col_lab + col) : -1);
+      s_epi[2 * BN + c] = __int_as_float(cl);
+      unsigned m = __ballot_sync(0xffffffffu, cl >= 0);
+      if ((c & 31) == 0) s_epi[3 * BN + (c >> 5)] = __uint_as_float(m);
     }
   }
   __device__ __forceinline__ void row_begin(int row, bool ok) {
     rinv_r = ok ? __ldg(p.rinv_row + row) : 0.f;
-    rs = expf(__ldg(p.logit_scale)) * kLog2e * rinv_r;
+    sl = expf(__ldg(p.logit_scale)) * kLog2e;
     lse2r = ok ? __ldg(p.lse2_row + row) : INFINITY;
     lab = ok ? __ldg(p.lab_row + row) : -1;
-    ci = __ldg(p.g_i) * p.inv_R;
-    ct = __ldg(p.g_t) * p.inv_P;
+    ci = ok ? __ldg(p.g_i) * p.inv_R : 0.f;     // rows past M contribute nothing
+    ct = ok ? __ldg(p.g_t) * p.inv_P : 0.f;
     dls = 0.f;
   }
   __device__ __forceinline__ void chunk(const float* acc, int col0, int lcol0, const float* s_epi,
@@ -128,15 +150,18 @@ struct EpiGrad {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const int col = col0 + i;
-      const float rc = s_epi[lcol0 + i];
-      const float v2 = acc[i] * rs * rc;
-      float g = ci * (ex2(v2 - lse2r) - (col == lab ? 1.f : 0.f));
-      const float cl = s_epi[BN + lcol0 + i];
+      const float rc = s_epi[lcol0 + i];       // 0 for columns past N: q = 0 kills g*q and g*v2
+      const float q = rinv_r * rc;
+      const float v2 = acc[i] * (q * sl);
+      float g = ci * ex2(v2 - lse2r);
+      if (col == lab) g -= ci;
       const int crow = __float_as_int(s_epi[2 * BN + lcol0 + i]);
-      g += ct * (ex2(v2 - cl) - (crow == row + p.row_offset ? 1.f : 0.f));
-      if (col >= p.N || !ok) g = 0.f;
-      dls += g * v2;
-      gs[i] = g * rinv_r * rc;
+      if (crow >= 0) {   // positive column: text-side term (uniform across the warp: same columns)
+        g += ct * ex2(v2 - s_epi[BN + lcol0 + i]);
+        if (crow == row + p.row_offset) g -= ct;
+      }
+      dls = fmaf(g, v2, dls);
+      gs[i] = g * q;
     }
     if (!ok) return;
     if constexpr (!TF32X3) {
@@ -174,11 +199,11 @@ struct EpiGrad {
       }
     }
   }
-  __device__ __forceinline__ void row_end(int, bool, int m_blk, int n_blk, int, float*, int et) {
+  __device__ __forceinline__ void row_end(int, bool, int m_blk, int n_blk, int, float*, int et, int half) {
     float v = warp_sum(dls);
     if ((et & 31) == 0) {
       int tile = n_blk * ((p.M + kBM - 1) / kBM) + m_blk;
-      p.dls_part[(int64_t)tile * 4 + (et >> 5)] = v;
+      p.dls_part[(int64_t)tile * 8 + half * 4 + (et >> 5)] = v;
     }
   }
 };
@@ -196,8 +221,8 @@ struct EpiStore {
   };
   Params p;
   float rs;
-  __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et) {
-    for (int c = et; c < BN; c += 128) {
+  __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et2) {
+    for (int c = et2; c < BN; c += kEpiThreads) {
       int col = n_blk * BN + c;
       s_epi[c] = (p.colscale != nullptr && col < p.N) ? __ldg(p.colscale + col) : 1.f;
     }
@@ -228,7 +253,7 @@ struct EpiStore {
       }
     }
   }
-  __device__ __forceinline__ void row_end(int, bool, int, int, int, float*, int) {}
+  __device__ __forceinline__ void row_end(int, bool, int, int, int, float*, int, int) {}
 };
 
 // ------------------------------------------------------------------------------------------
@@ -508,11 +533,11 @@ CtrWs carve(void* base, int R, int C, int P, int D, int dtype) {
   w.col_lse2 = cv.take<float>(C);
   w.lab_local = cv.take<int>(R); w.col_lab = cv.take<int>(C); w.lab_t = cv.take<int>(P);
   w.lab_logit_i = cv.take<float>(R); w.lab_logit_t = cv.take<float>(P);
-  w.part_i = cv.take<float2>((size_t)R * w.nblk_i);
-  w.part_t = cv.take<float2>((size_t)P * w.nblk_t);
+  w.part_i = cv.take<float2>((size_t)R * w.nblk_i * 2);
+  w.part_t = cv.take<float2>((size_t)P * w.nblk_t * 2);
   w.row_part = cv.take<float4>(R);
   w.sums = cv.take<float>(4);
-  w.dls_part = cv.take<float>((size_t)w.tiles_g * 4);
+  w.dls_part = cv.take<float>((size_t)w.tiles_g * 8);
   if (dtype == CE_F32) {
     for (int i = 0; i < 2; ++i) {
       w.img_p[i] = cv.take<float>((size_t)R * D);
@@ -582,8 +607,8 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const in
     typename EpiStats<BN>::Params ep{w.rinv_p, w.rinv_i, ls, w.part_t, P, R, w.nblk_t, w.lab_t, w.lab_logit_t};
     CE_TRY((launch_gemm<TF, BN, EpiStats<BN>>(op, oi, D, 1, ep, st)));
   }
-  ItemArgs ia{img, txt, ls, labels_i, labels_t, index_pos, w.rinv_i, w.rinv_t, w.part_i, w.nblk_i,
-              w.part_t, w.nblk_t, R, C, P, D, col_offset, reinterpret_cast<float4*>(row_part),
+  ItemArgs ia{img, txt, ls, labels_i, labels_t, index_pos, w.rinv_i, w.rinv_t, w.part_i, 2 * w.nblk_i,
+              w.part_t, 2 * w.nblk_t, R, C, P, D, col_offset, reinterpret_cast<float4*>(row_part),
               w.lab_logit_i, w.lab_logit_t, w.lse2_col, w.item_t};
   int blocks = ((R + P) * 32 + 255) / 256;
   fwd_items_kernel<DT><<<blocks, 256, 0, st>>>(ia);
@@ -630,7 +655,7 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const in
     ep.num_tiles = w.tiles_g;
     CE_TRY((launch_gemm<TF, BN, EpiGrad<BN, TF>>(oi, ot, D, 1, ep, st)));
   }
-  sum_dls_kernel<<<1, 1024, 0, st>>>(w.dls_part, w.tiles_g * 4, dls_out);
+  sum_dls_kernel<<<1, 1024, 0, st>>>(w.dls_part, w.tiles_g * 8, dls_out);
   CE_LAUNCH_CHECK();
   // d I^ (partial over local columns) = s |i| (G'' txt):  A = G'' [R, C] K-major, B = txt [C, D] MN-major
   GemmOperand gA = operand<DT>(w.G[0], w.G, R, w.ldg, 0);

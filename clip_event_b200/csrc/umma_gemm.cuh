@@ -4,8 +4,9 @@
 //   128-byte-swizzled shared memory, `tcgen05.mma` issued by one thread, accumulators double
 //   buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4..7 = epilogue (TMEM lanes 32*(warp%4) ..).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..11 = epilogue: warp w reads TMEM lanes 32*(w%4).. and the column half
+// (w-4)/4 of the tile, so two warps share each row.
 //
 // Operand precision: bf16 (kind::f16, one product) or fp32 carried as a (hi, lo) pair of tf32
 // arrays with three products hi*hi + hi*lo + lo*hi (kind::tf32) -- fp32-level accuracy.
@@ -22,7 +23,8 @@ namespace ce {
 
 constexpr int kBM = 128;           // tile rows (UMMA M)
 constexpr int kSwizzleBytes = 128; // one swizzle atom = BLOCK_K
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 
 struct GemmShape {
   int M, N, K;             // problem extents (rows of A, rows of B, reduction)
@@ -90,7 +92,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -186,15 +188,18 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
   } else if (warp >= 4) {
     // ================= epilogue =================
     Epi epi{ep};
-    const int q = warp - 4;             // TMEM lane quadrant
+    const int q = (warp - 4) & 3;       // TMEM lane quadrant
+    const int half = (warp - 4) >> 2;   // column half of the tile
     const int et = q * 32 + lane;       // 0..127 = row inside the tile
+    const int et2 = (warp - 4) * 32 + lane;  // 0..255 among the epilogue threads
+    constexpr int kChunksPerHalf = BN / 64;
     int acc_stage = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int tile = item % num_tiles, ksp = item / num_tiles;
       const int m_blk = tile % gs.num_m_blk, n_blk = tile / gs.num_m_blk;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's s_epi fully consumed
-      epi.tile_begin(s_epi, m_blk, n_blk, et);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's s_epi fully consumed
+      epi.tile_begin(s_epi, m_blk, n_blk, et2);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const int row = m_blk * kBM + et;
       const bool row_ok = row < gs.M;
       epi.row_begin(row, row_ok);
@@ -202,7 +207,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_stage * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * kChunksPerHalf; c < (half + 1) * kChunksPerHalf; ++c) {
         float acc[32];
         tmem_ld32(taddr + c * 32, acc);
         tmem_ld_wait();
@@ -211,7 +216,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc_stage]);
-      epi.row_end(row, row_ok, m_blk, n_blk, ksp, s_epi, et);
+      epi.row_end(row, row_ok, m_blk, n_blk, ksp, s_epi, et, half);
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   }
