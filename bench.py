@@ -244,10 +244,10 @@ def main():
     torch.cuda.synchronize()
 
     graph = None
-    if not args.no_graph and world == 1:   # NCCL collectives stay eager (graph capture of the exchange is future work)
+    if not args.no_graph:   # the NCCL exchange is captured too (thread-local capture: the NCCL watchdog thread stays legal)
         try:
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 step()
             torch.cuda.synchronize()
         except Exception as e:  # pragma: no cover
@@ -334,7 +334,7 @@ def main():
 
     def graphed(fn):
         """Replayable CUDA graph of one chain (eager launches on a slow host would time the host)."""
-        if args.no_graph or world > 1:
+        if args.no_graph:
             return fn
         try:
             s_ = torch.cuda.Stream()
@@ -344,7 +344,7 @@ def main():
             torch.cuda.current_stream().wait_stream(s_)
             torch.cuda.synchronize()
             g_ = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_):
+            with torch.cuda.graph(g_, capture_error_mode="thread_local"):
                 fn()
             torch.cuda.synchronize()
             return g_.replay
@@ -413,9 +413,15 @@ def main():
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # destroy_process_group() blocks after NCCL work was replayed from CUDA graphs; everything is
+        # already synchronised and printed, so leave without the teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
