@@ -208,21 +208,34 @@ def main():
     losses_out = torch.zeros(3, dtype=torch.float32, device=dev)
     losses_host = torch.zeros(3, dtype=torch.float32).pin_memory()
 
+    ot_stream = torch.cuda.Stream()
+
     def step():
-        """fwd + bwd of the loss head exactly as engine.py:48-67,88 drives it."""
+        """fwd + bwd of the loss head as engine.py:48-67,88 drives it.  The two criteria are
+        independent until the final sum, so the OT criterion is issued on a second stream: its
+        ALU/HBM-bound kernels overlap the tensor-core GEMMs and the NCCL latencies (autograd runs
+        each backward on the stream of its forward)."""
         for t in leaves.values():
             t.grad = None
         head.logit_scale.grad = None
+        main = torch.cuda.current_stream()
+        ot_stream.wait_stream(main)
+        with torch.cuda.stream(ot_stream):
+            if world > 1:
+                loss_ot = cd.sharded_alignment(leaves["etxt"], leaves["obj"], static["tnum"], static["onum"])
+            else:
+                loss_ot = crit_ot(leaves["etxt"], leaves["obj"], static["tnum"], static["onum"])["loss_ot"]
         if world > 1:
             li, lt = cd.global_contrastive(leaves["img"], leaves["txt"], head.logit_scale, lpi, lpt, idx)
-            lo_ = cd.sharded_alignment(leaves["etxt"], leaves["obj"], static["tnum"], static["onum"])
-            loss_dict = {"loss_i": li, "loss_t": lt, "loss_ot": lo_}
+            loss_dict = {"loss_i": li, "loss_t": lt}
         else:
             a, b_ = head(leaves["img"], leaves["txt"])
             loss_dict = crit(a, b_, lpi, lpt, index_pos=idx, constrastive_overbatch=True)
-            loss_dict.update(crit_ot(leaves["etxt"], leaves["obj"], static["tnum"], static["onum"]))
+        main.wait_stream(ot_stream)
+        loss_dict["loss_ot"] = loss_ot
         total = sum(v.float() for v in loss_dict.values())
         total.backward()
+        main.wait_stream(ot_stream)
         losses_out.copy_(torch.stack([loss_dict["loss_i"].float(), loss_dict["loss_t"].float(),
                                       loss_dict["loss_ot"].float()]))
 

@@ -13,6 +13,8 @@
 //             two more tcgen05 GEMMs give s*G*T^ and s*G^t*I^, and a row kernel applies the
 //             normalisation backward.
 // Inverse norms, exp(logit_scale) and log2(e) are folded into the epilogue scale factors.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "umma_gemm.cuh"
@@ -98,6 +100,10 @@ struct EpiStats {
   }
 };
 
+// Row-softmax gradient: G[r,c] = coef * (softmax_row(L)[r,c] - [c == lab[r]]) * rinv_row[r] * rinv_col[c]
+// (both inverse norms folded in so that the following GEMMs run on the RAW embeddings).
+// The backward of the over-batch loss is two such problems: (images x descriptions, image-side
+// cross-entropy) and (positive descriptions x images, text-side cross-entropy).
 template <int BN, bool TF32X3>
 struct EpiGrad {
   struct Params {
@@ -105,63 +111,74 @@ struct EpiGrad {
     const float* rinv_col;
     const float* logit_scale;
     const float* lse2_row;   // [M]  base-2 row LSE (global, after the cross-rank merge)
-    const int* lab_row;      // [M]  local column of the row's positive, or -1
-    const float* col_lse2;   // [N]  base-2 column LSE at positive columns, +inf elsewhere
-    const int* col_lab;      // [N]  global row of the column's positive image, or -1
-    const float* g_i;
-    const float* g_t;
-    float inv_R, inv_P;
-    int row_offset;          // global index of row 0 (0: rows are always the full gathered set)
+    const int* lab_row;      // [M]  column of the row's positive, or -1
+    const float* g;          // device scalar dL/dloss
+    float inv_count;         // 1 / (number of rows in the GLOBAL mean)
     void* G0;                // bf16 [M, ldg]  or tf32-hi fp32 [M, ldg]
     void* G1;                // tf32-lo
     int64_t ldg;
     float* dls_part;         // [tiles, 8]
-    int M, N, num_tiles;
+    int M, N;
   };
   Params p;
-  float sl, rinv_r, lse2r, ci, ct, dls;
+  // Per element: t = kr*rc ; v = acc*t - lse (base-2 log-probability) ; g' = cs * 2^v ;
+  // G = g' * t ; dls' += g' * v.   Here kr = s*log2e/|row|, cs = coef/(s*log2e), so that
+  // g'*t = coef*softmax/(|row||col|) and sum(g*L) = s*log2e*ln2 * sum(g'*(v + lse)); the lse part
+  // vanishes because a softmax-minus-one-hot row sums to zero.
+  float sl, kr, lse2r, cs, dls;
   int lab;
-  // s_epi layout: [0,BN) rinv_col, [BN,2BN) col_lse2, [2BN,3BN) col_lab (int bits),
-  //               [3BN, 3BN+BN/32) bitmask of positive columns per 32-column chunk
   __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et2) {
     for (int c = et2; c < BN; c += kEpiThreads) {
       int col = n_blk * BN + c;
-      bool ok = col < p.N;
-      int cl = ok ? __ldg(p.col_lab + col) : -1;
-      s_epi[c] = ok ? __ldg(p.rinv_col + col) : 0.f;
-      s_epi[BN + c] = ok ? __ldg(p.col_lse2 + col) : INFINITY;
-      s_epi[2 * BN + c] = __int_as_float(cl);
-      unsigned m = __ballot_sync(0xffffffffu, cl >= 0);
-      if ((c & 31) == 0) s_epi[3 * BN + (c >> 5)] = __uint_as_float(m);
+      s_epi[c] = col < p.N ? __ldg(p.rinv_col + col) : 0.f;
     }
   }
   __device__ __forceinline__ void row_begin(int row, bool ok) {
-    rinv_r = ok ? __ldg(p.rinv_row + row) : 0.f;
     sl = expf(__ldg(p.logit_scale)) * kLog2e;
-    lse2r = ok ? __ldg(p.lse2_row + row) : INFINITY;
+    kr = ok ? sl * __ldg(p.rinv_row + row) : 0.f;
+    lse2r = ok ? __ldg(p.lse2_row + row) : 0.f;        // rows past M: v = 0, g = cs * 1 = 0
     lab = ok ? __ldg(p.lab_row + row) : -1;
-    ci = ok ? __ldg(p.g_i) * p.inv_R : 0.f;     // rows past M contribute nothing
-    ct = ok ? __ldg(p.g_t) * p.inv_P : 0.f;
+    cs = ok ? __ldg(p.g) * p.inv_count / sl : 0.f;
     dls = 0.f;
   }
   __device__ __forceinline__ void chunk(const float* acc, int col0, int lcol0, const float* s_epi,
                                         int row, bool ok) {
     float gs[32];
+    const float4* rc4 = reinterpret_cast<const float4*>(s_epi + lcol0);
+    if (col0 + 32 <= p.N) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int col = col0 + i;
-      const float rc = s_epi[lcol0 + i];       // 0 for columns past N: q = 0 kills g*q and g*v2
-      const float q = rinv_r * rc;
-      const float v2 = acc[i] * (q * sl);
-      float g = ci * ex2(v2 - lse2r);
-      if (col == lab) g -= ci;
-      const int crow = __float_as_int(s_epi[2 * BN + lcol0 + i]);
-      if (crow >= 0) {   // positive column: text-side term (uniform across the warp: same columns)
-        g += ct * ex2(v2 - s_epi[BN + lcol0 + i]);
-        if (crow == row + p.row_offset) g -= ct;
+      for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 r4 = rc4[i4];
+        const float rcv[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = 4 * i4 + j;
+          const float t = kr * rcv[j];
+          const float v = fmaf(acc[i], t, -lse2r);
+          const float g = cs * ex2(v);
+          dls = fmaf(g, v, dls);
+          gs[i] = g * t;
+        }
       }
-      dls = fmaf(g, v2, dls);
-      gs[i] = g * q;
+    } else {   // last, ragged column tile: columns past N must not contribute
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float t = kr * s_epi[lcol0 + i];
+        const float v = fmaf(acc[i], t, -lse2r);
+        const float g = (col0 + i < p.N) ? cs * ex2(v) : 0.f;
+        dls = fmaf(g, v, dls);
+        gs[i] = g * t;
+      }
+    }
+    if ((unsigned)(lab - col0) < 32u) {   // the one-hot: at most one chunk per row
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (col0 + i == lab) {
+          const float t = kr * s_epi[lcol0 + i];
+          gs[i] = fmaf(-cs, t, gs[i]);
+          dls = fmaf(-cs, fmaf(acc[i], t, -lse2r), dls);
+        }
+      }
     }
     if (!ok) return;
     if constexpr (!TF32X3) {
@@ -200,7 +217,7 @@ struct EpiGrad {
     }
   }
   __device__ __forceinline__ void row_end(int, bool, int m_blk, int n_blk, int, float*, int et, int half) {
-    float v = warp_sum(dls);
+    float v = warp_sum(dls * sl);
     if ((et & 31) == 0) {
       int tile = n_blk * ((p.M + kBM - 1) / kBM) + m_blk;
       p.dls_part[(int64_t)tile * 8 + half * 4 + (et >> 5)] = v;
@@ -216,7 +233,7 @@ struct EpiStore {
     const float* rowscale;     // nullable
     const float* colscale;     // nullable
     const float* logit_scale;  // nullable: alpha = exp(*logit_scale)
-    int atomic;                // accumulate with red.add (split-K)
+    int atomic;                // 1: accumulate with red.add (split-K); 2: exclusive tile, out += v
     int M, N;
   };
   Params p;
@@ -235,19 +252,25 @@ struct EpiStore {
                                         int row, bool ok) {
     if (!ok) return;
     float* o = p.out + (int64_t)row * p.ldo + col0;
-    const bool vec = (p.ldo % 4 == 0) && (col0 + 32 <= p.N) && !p.atomic;
+    const bool vec = (p.ldo % 4 == 0) && (col0 + 32 <= p.N) && p.atomic != 1;
     if (vec) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        *reinterpret_cast<float4*>(o + i) =
-            make_float4(acc[i] * rs * s_epi[lcol0 + i], acc[i + 1] * rs * s_epi[lcol0 + i + 1],
-                        acc[i + 2] * rs * s_epi[lcol0 + i + 2], acc[i + 3] * rs * s_epi[lcol0 + i + 3]);
+      for (int i = 0; i < 32; i += 4) {
+        float4 v = make_float4(acc[i] * rs * s_epi[lcol0 + i], acc[i + 1] * rs * s_epi[lcol0 + i + 1],
+                               acc[i + 2] * rs * s_epi[lcol0 + i + 2], acc[i + 3] * rs * s_epi[lcol0 + i + 3]);
+        if (p.atomic == 2) {
+          const float4 old = *reinterpret_cast<const float4*>(o + i);
+          v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+        }
+        *reinterpret_cast<float4*>(o + i) = v;
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         if (col0 + i < p.N) {
           float v = acc[i] * rs * s_epi[lcol0 + i];
-          if (p.atomic) atomicAdd(o + i, v);
+          if (p.atomic == 1) atomicAdd(o + i, v);
+          else if (p.atomic == 2) o[i] += v;
           else o[i] = v;
         }
       }
@@ -437,18 +460,22 @@ __global__ void __launch_bounds__(1024) fwd_finish_kernel(const float4* row_part
   }
 }
 
-__global__ void col_fill_kernel(float* col_lse2, int* col_lab, int C) {
+// col_pos[c] = p if description c is the p-th positive (index_pos[p] == c), else -1
+__global__ void col_pos_fill_kernel(int* col_pos, int C) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) { col_lse2[c] = INFINITY; col_lab[c] = -1; }
+  if (c < C) col_pos[c] = -1;
 }
-__global__ void col_scatter_kernel(const int64_t* index_pos, const int64_t* labels_t,
-                                   const float* lse2_col, int P, float* col_lse2, int* col_lab) {
+__global__ void col_pos_scatter_kernel(const int64_t* index_pos, int P, int* col_pos) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P) {
-    int64_t c = index_pos[p];
-    col_lse2[c] = lse2_col[p];
-    col_lab[c] = (int)labels_t[c];
-  }
+  if (p < P) col_pos[index_pos[p]] = p;
+}
+
+// rows of dpos_hat *= |t_pos|  (one warp per row)
+__global__ void pos_scale_kernel(float* dpos, const int64_t* index_pos, const float* norm_t, int P, int D) {
+  int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (p >= P) return;
+  const float s = norm_t[index_pos[p]];
+  for (int c = lane; c < D; c += 32) dpos[(int64_t)p * D + c] *= s;
 }
 
 __global__ void __launch_bounds__(1024) sum_dls_kernel(const float* part, int n, float* out) {
@@ -467,8 +494,11 @@ __global__ void __launch_bounds__(1024) sum_dls_kernel(const float* part, int n,
 }
 
 // dx = (d - x^ (x^ . d)) / |x|, one warp per row (model_clip.py:496-497 backward).
+// `extra` (optional): per-row index into a second fp32 matrix whose row is added to d first (the
+// text-side gradient of a positive description).
 template <int DT>
-__global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, int D, void* out) {
+__global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, int D, void* out,
+                                     const int* extra_idx, const float* extra) {
   using T = typename In<DT>::type;
   constexpr int V = In<DT>::kVec;
   int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -476,12 +506,18 @@ __global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, 
   if (r >= rows) return;
   const T* x = reinterpret_cast<const T*>(xin) + (int64_t)r * D;
   const float* dr = d + (int64_t)r * D;
+  const int ei = extra_idx != nullptr ? extra_idx[r] : -1;
+  const float* er = ei >= 0 ? extra + (int64_t)ei * D : nullptr;
   float n2 = 0.f, dot = 0.f;
   for (int c = lane * V; c < D; c += 32 * V) {
     float v[8];
     In<DT>::load16(x + c, v);
 #pragma unroll
-    for (int i = 0; i < V; ++i) { n2 += v[i] * v[i]; dot += v[i] * dr[c + i]; }
+    for (int i = 0; i < V; ++i) {
+      float dv = dr[c + i] + (er != nullptr ? er[c + i] : 0.f);
+      n2 += v[i] * v[i];
+      dot += v[i] * dv;
+    }
   }
   n2 = warp_sum(n2);
   dot = warp_sum(dot);
@@ -493,7 +529,10 @@ __global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, 
     float v[8];
     In<DT>::load16(x + c, v);
 #pragma unroll
-    for (int i = 0; i < V; ++i) In<DT>::st(o + c + i, (dr[c + i] - v[i] * coef) * rinv);
+    for (int i = 0; i < V; ++i) {
+      float dv = dr[c + i] + (er != nullptr ? er[c + i] : 0.f);
+      In<DT>::st(o + c + i, (dv - v[i] * coef) * rinv);
+    }
   }
 }
 
@@ -502,17 +541,18 @@ __global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, 
 // ------------------------------------------------------------------------------------------
 struct CtrWs {
   float *rinv_i, *norm_i, *rinv_t, *norm_t, *rinv_p;
-  float *lse2_row, *lse2_col, *item_t, *col_lse2;
-  int *lab_local, *col_lab, *lab_t;
+  float *lse2_row, *lse2_col, *item_t;
+  int *lab_local, *col_pos, *lab_t;
   float *lab_logit_i, *lab_logit_t;
   float2 *part_i, *part_t;
   float4* row_part;
   float *sums, *dls_part;
   void *img_p[2], *txt_p[2], *pos_p[2];
-  void* G[2];
-  float *dtxt_hat, *dimg_hat;
-  int64_t ldg;
-  int nblk_i, nblk_t, tiles_g;
+  void* G[2];      // image-side gradient matrix [R, ldg]
+  void* Gt[2];     // text-side  gradient matrix [P, ldgt]
+  float *dtxt_hat, *dimg_hat, *dpos_hat;
+  int64_t ldg, ldgt;
+  int nblk_i, nblk_t, tiles_g, tiles_gt;
   size_t bytes;
 };
 
@@ -526,18 +566,18 @@ CtrWs carve(void* base, int R, int C, int P, int D, int dtype) {
   w.nblk_i = (C + BN - 1) / BN;
   w.nblk_t = (R + BN - 1) / BN;
   w.tiles_g = ((R + kBM - 1) / kBM) * w.nblk_i;
+  w.tiles_gt = ((P + kBM - 1) / kBM) * w.nblk_t;
   w.rinv_i = cv.take<float>(R); w.norm_i = cv.take<float>(R);
   w.rinv_t = cv.take<float>(C); w.norm_t = cv.take<float>(C);
   w.rinv_p = cv.take<float>(P);
   w.lse2_row = cv.take<float>(R); w.lse2_col = cv.take<float>(P); w.item_t = cv.take<float>(P);
-  w.col_lse2 = cv.take<float>(C);
-  w.lab_local = cv.take<int>(R); w.col_lab = cv.take<int>(C); w.lab_t = cv.take<int>(P);
+  w.lab_local = cv.take<int>(R); w.col_pos = cv.take<int>(C); w.lab_t = cv.take<int>(P);
   w.lab_logit_i = cv.take<float>(R); w.lab_logit_t = cv.take<float>(P);
   w.part_i = cv.take<float2>((size_t)R * w.nblk_i * 2);
   w.part_t = cv.take<float2>((size_t)P * w.nblk_t * 2);
   w.row_part = cv.take<float4>(R);
   w.sums = cv.take<float>(4);
-  w.dls_part = cv.take<float>((size_t)w.tiles_g * 8);
+  w.dls_part = cv.take<float>((size_t)(w.tiles_g + w.tiles_gt) * 8);
   if (dtype == CE_F32) {
     for (int i = 0; i < 2; ++i) {
       w.img_p[i] = cv.take<float>((size_t)R * D);
@@ -545,15 +585,21 @@ CtrWs carve(void* base, int R, int C, int P, int D, int dtype) {
       w.pos_p[i] = cv.take<float>((size_t)P * D);
     }
     w.ldg = (C + 3) / 4 * 4;
+    w.ldgt = (R + 3) / 4 * 4;
     w.G[0] = cv.take<float>((size_t)R * w.ldg);
     w.G[1] = cv.take<float>((size_t)R * w.ldg);
+    w.Gt[0] = cv.take<float>((size_t)P * w.ldgt);
+    w.Gt[1] = cv.take<float>((size_t)P * w.ldgt);
   } else {
     w.pos_p[0] = cv.take<__nv_bfloat16>((size_t)P * D);
     w.ldg = (C + 7) / 8 * 8;
+    w.ldgt = (R + 7) / 8 * 8;
     w.G[0] = cv.take<__nv_bfloat16>((size_t)R * w.ldg);
+    w.Gt[0] = cv.take<__nv_bfloat16>((size_t)P * w.ldgt);
   }
   w.dtxt_hat = cv.take<float>((size_t)C * D);
   w.dimg_hat = cv.take<float>((size_t)R * D);
+  w.dpos_hat = cv.take<float>((size_t)P * D);
   w.bytes = cv.used() + 1024;
   return w;
 }
@@ -619,18 +665,32 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const in
 }
 
 // C[M,N] fp32 = alpha * rowscale * (A B^t) with split-K when the tile count cannot fill the GPU.
-template <bool TF>
-int plain_gemm(const GemmOperand& A, const GemmOperand& B, int K, float* out, int64_t ldo,
-               const float* rowscale, const float* ls, cudaStream_t st) {
-  constexpr int BN = TF ? 128 : 256;
+// C[M,N] fp32 = alpha * rowscale * (A B^t).  Narrow tiles when the wide ones cannot fill the GPU,
+// split-K (red.add into a zeroed buffer) only when even those cannot.  `accumulate`: add into `out`.
+template <bool TF, int BN>
+int plain_gemm_bn(const GemmOperand& A, const GemmOperand& B, int K, float* out, int64_t ldo,
+                  const float* rowscale, const float* ls, bool accumulate, cudaStream_t st) {
   using Cfg = GemmCfg<TF, BN>;
   int tiles = ((A.rows + kBM - 1) / kBM) * ((B.rows + BN - 1) / BN);
   int kblk = (K + Cfg::kBK - 1) / Cfg::kBK;
   int splits = 1;
-  if (tiles < num_sms()) splits = std::max(1, std::min({num_sms() / tiles, kblk / 8, 16}));
-  if (splits > 1) CE_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)A.rows * ldo, st));
-  typename EpiStore<BN>::Params ep{out, ldo, rowscale, nullptr, ls, splits > 1 ? 1 : 0, A.rows, B.rows};
+  if (tiles * 2 <= num_sms()) splits = std::max(1, std::min({num_sms() / tiles, kblk / 8, 16}));
+  if (splits > 1 && !accumulate) CE_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)A.rows * ldo, st));
+  static const int acc_mode = getenv("CE_ACC_MODE") ? atoi(getenv("CE_ACC_MODE")) : 2;   // tuning aid
+  typename EpiStore<BN>::Params ep{out, ldo, rowscale, nullptr, ls, splits > 1 ? 1 : (accumulate ? acc_mode : 0), A.rows, B.rows};
   return launch_gemm<TF, BN, EpiStore<BN>>(A, B, K, splits, ep, st);
+}
+template <bool TF>
+int plain_gemm(const GemmOperand& A, const GemmOperand& B, int K, float* out, int64_t ldo,
+               const float* rowscale, const float* ls, bool accumulate, cudaStream_t st) {
+  if constexpr (TF) {
+    return plain_gemm_bn<true, 128>(A, B, K, out, ldo, rowscale, ls, accumulate, st);
+  } else {
+    // wide tiles unless they leave most SMs idle AND the reduction is too short to split
+    int wide = ((A.rows + kBM - 1) / kBM) * ((B.rows + 255) / 256);
+    if (wide * 2 > num_sms() || K >= 16384) return plain_gemm_bn<false, 256>(A, B, K, out, ldo, rowscale, ls, accumulate, st);
+    return plain_gemm_bn<false, 128>(A, B, K, out, ldo, rowscale, ls, accumulate, st);
+  }
 }
 
 template <int DT>
@@ -638,34 +698,47 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const in
                      const int64_t* index_pos, int R, int C, int P, int D, const float* g_i,
                      const float* g_t, int R_total, int P_total, void* dtxt, float* dimg_hat_part,
                      float* dls_out, CtrWs& w, cudaStream_t st) {
+  (void)labels_t;
   constexpr bool TF = DT == CE_F32;
   constexpr int BN = s_bn<DT>();
-  col_fill_kernel<<<(C + 255) / 256, 256, 0, st>>>(w.col_lse2, w.col_lab, C);
+  col_pos_fill_kernel<<<(C + 255) / 256, 256, 0, st>>>(w.col_pos, C);
   CE_LAUNCH_CHECK();
-  col_scatter_kernel<<<(P + 255) / 256, 256, 0, st>>>(index_pos, labels_t, w.lse2_col, P, w.col_lse2, w.col_lab);
+  col_pos_scatter_kernel<<<(P + 255) / 256, 256, 0, st>>>(index_pos, P, w.col_pos);
   CE_LAUNCH_CHECK();
   GemmOperand oi = operand<DT>(img, w.img_p, R, D, 0);
   GemmOperand ot = operand<DT>(txt, w.txt_p, C, D, 0);
-  {
+  GemmOperand op = operand<DT>(w.pos_p[0], w.pos_p, P, D, 0);
+  {  // image side: rows = images, columns = local descriptions
     typename EpiGrad<BN, TF>::Params ep{};
     ep.rinv_row = w.rinv_i; ep.rinv_col = w.rinv_t; ep.logit_scale = ls; ep.lse2_row = w.lse2_row;
-    ep.lab_row = w.lab_local; ep.col_lse2 = w.col_lse2; ep.col_lab = w.col_lab; ep.g_i = g_i; ep.g_t = g_t;
-    ep.inv_R = 1.f / (float)R_total; ep.inv_P = 1.f / (float)P_total; ep.row_offset = 0;
+    ep.lab_row = w.lab_local; ep.g = g_i; ep.inv_count = 1.f / (float)R_total;
     ep.G0 = w.G[0]; ep.G1 = w.G[1]; ep.ldg = w.ldg; ep.dls_part = w.dls_part; ep.M = R; ep.N = C;
-    ep.num_tiles = w.tiles_g;
     CE_TRY((launch_gemm<TF, BN, EpiGrad<BN, TF>>(oi, ot, D, 1, ep, st)));
   }
-  sum_dls_kernel<<<1, 1024, 0, st>>>(w.dls_part, w.tiles_g * 8, dls_out);
+  {  // text side: rows = local positive descriptions, columns = images
+    typename EpiGrad<BN, TF>::Params ep{};
+    ep.rinv_row = w.rinv_p; ep.rinv_col = w.rinv_i; ep.logit_scale = ls; ep.lse2_row = w.lse2_col;
+    ep.lab_row = w.lab_t; ep.g = g_t; ep.inv_count = 1.f / (float)P_total;
+    ep.G0 = w.Gt[0]; ep.G1 = w.Gt[1]; ep.ldg = w.ldgt; ep.dls_part = w.dls_part + (size_t)w.tiles_g * 8;
+    ep.M = P; ep.N = R;
+    CE_TRY((launch_gemm<TF, BN, EpiGrad<BN, TF>>(op, oi, D, 1, ep, st)));
+  }
+  sum_dls_kernel<<<1, 1024, 0, st>>>(w.dls_part, (w.tiles_g + w.tiles_gt) * 8, dls_out);
   CE_LAUNCH_CHECK();
-  // d I^ (partial over local columns) = s |i| (G'' txt):  A = G'' [R, C] K-major, B = txt [C, D] MN-major
-  GemmOperand gA = operand<DT>(w.G[0], w.G, R, w.ldg, 0);
-  GemmOperand tB = operand<DT>(txt, w.txt_p, D, D, 1);
-  CE_TRY((plain_gemm<TF>(gA, tB, C, dimg_hat_part, D, w.norm_i, ls, st)));
-  // d T^ = s |t| (G''^t img):  A = G'' as [K=R, M=C] MN-major, B = img [R, D] MN-major
-  GemmOperand gAt = operand<DT>(w.G[0], w.G, C, w.ldg, 1);
-  GemmOperand iB = operand<DT>(img, w.img_p, D, D, 1);
-  CE_TRY((plain_gemm<TF>(gAt, iB, R, w.dtxt_hat, D, w.norm_t, ls, st)));
-  normalize_bwd_kernel<DT><<<(C * 32 + 255) / 256, 256, 0, st>>>(txt, w.dtxt_hat, C, D, dtxt);
+  GemmOperand tB = operand<DT>(txt, w.txt_p, D, D, 1);          // [K = C, N = D]
+  GemmOperand iB = operand<DT>(img, w.img_p, D, D, 1);          // [K = R, N = D]
+  GemmOperand pB = operand<DT>(w.pos_p[0], w.pos_p, D, D, 1);   // [K = P, N = D]
+  // d I^ (partial over the local columns) = s |i| (G txt + Gt^t pos)
+  CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, R, w.ldg, 0), tB, C, dimg_hat_part, D, w.norm_i, ls, false, st)));
+  CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, R, w.ldgt, 1), pB, P, dimg_hat_part, D, w.norm_i, ls, true, st)));
+  // d T^ = s |t| G^t img  (+ s |t_pos| Gt img on the positive rows, added by the row kernel)
+  CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, C, w.ldg, 1), iB, R, w.dtxt_hat, D, w.norm_t, ls, false, st)));
+  CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, P, w.ldgt, 0), iB, R, w.dpos_hat, D, nullptr, ls, false, st)));
+  // dpos_hat rows still miss the |t_pos| factor: norm_t[index_pos[p]]; fold it in the row kernel via
+  // the same normalisation (x^ . d and the final 1/|x| are linear in d) -- see normalize_bwd_kernel.
+  pos_scale_kernel<<<(P * 32 + 255) / 256, 256, 0, st>>>(w.dpos_hat, index_pos, w.norm_t, P, D);
+  CE_LAUNCH_CHECK();
+  normalize_bwd_kernel<DT><<<(C * 32 + 255) / 256, 256, 0, st>>>(txt, w.dtxt_hat, C, D, dtxt, w.col_pos, w.dpos_hat);
   CE_LAUNCH_CHECK();
   return CE_OK;
 }
@@ -735,8 +808,8 @@ extern "C" int ce_contrastive_bwd_finish(const void* img_rows, const float* dimg
   if (rows == 0) return CE_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int blocks = (rows * 32 + 255) / 256;
-  if (dtype == CE_F32) normalize_bwd_kernel<CE_F32><<<blocks, 256, 0, st>>>(img_rows, dimg_hat_rows, rows, D, dimg_rows);
-  else normalize_bwd_kernel<CE_BF16><<<blocks, 256, 0, st>>>(img_rows, dimg_hat_rows, rows, D, dimg_rows);
+  if (dtype == CE_F32) normalize_bwd_kernel<CE_F32><<<blocks, 256, 0, st>>>(img_rows, dimg_hat_rows, rows, D, dimg_rows, nullptr, nullptr);
+  else normalize_bwd_kernel<CE_BF16><<<blocks, 256, 0, st>>>(img_rows, dimg_hat_rows, rows, D, dimg_rows, nullptr, nullptr);
   CE_LAUNCH_CHECK();
   return CE_OK;
 }

@@ -67,6 +67,11 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t* r, const void* row_ptr) 
                : "=r"(r[0]), "=r"(r[1])
                : "r"(smem_u32(row_ptr)));
 }
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const void* row_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(row_ptr)));
+}
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -322,8 +327,11 @@ __device__ __forceinline__ float frcp(float x) {
 //   RP   = G/TC image rows per pass, RPT passes
 // SCHEME 0: every thread sums the warps' column partials itself (1 barrier / iteration)
 // SCHEME 1: warp 0 sums them and publishes sigma (2 barriers / iteration, fewer instructions)
-template <int MP, int RPT, int G, int MINB = 1, int SCHEME = 0>
+// ASM: keep the kernel matrix A in (dynamic) shared memory instead of registers -- for plans too large
+// for 2 x RPT x 4 registers per thread (64 x 577).
+template <int MP, int RPT, int G, int MINB = 1, int SCHEME = 0, bool ASM = false>
 __global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(IpotArgs a) {
+  extern __shared__ __align__(16) float s_A[];     // [RPT*RP][MP] when ASM
   constexpr int TC = MP / 4;
   constexpr int RP = G / TC;
   constexpr int BT = G < 256 ? 256 : G;   // threads per CTA
@@ -381,7 +389,7 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(Ipot
   const bool empty = (xlen == 0.f || ylen == 0.f);   // model_ot.py:62: whole plan masked -> 0
 
   // ---- kernel matrix A = exp(-C/beta), R = 1 on valid pairs ----------------------------------
-  float2 A[RPT][2], R[RPT][2];
+  float2 A[ASM ? 1 : RPT][2], R[RPT][2];
   float u[RPT];
   constexpr int NG = (RPT + TC - 1) / TC;   // groups of TC rows; lane tc owns row gi*TC + tc of group gi
   float uown[NG], ygown[NG], zown[NG];
@@ -406,7 +414,11 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(Ipot
       bool valid = !((ypad >> i) & 1u) && xg[j] == 0.f && !empty;
       av[j] = valid ? expf((1.f - sv[j] * rx[j] * ryi) * nib) : 0.f;
     }
-    A[i][0] = f2(av[0], av[1]); A[i][1] = f2(av[2], av[3]);
+    if constexpr (ASM) {
+      *reinterpret_cast<float4*>(s_A + (size_t)(tr + i * RP) * MP + m0) = make_float4(av[0], av[1], av[2], av[3]);
+    } else {
+      A[i][0] = f2(av[0], av[1]); A[i][1] = f2(av[2], av[3]);
+    }
     R[i][0] = f2(av[0] != 0.f ? 1.f : 0.f, av[1] != 0.f ? 1.f : 0.f);
     R[i][1] = f2(av[2] != 0.f ? 1.f : 0.f, av[3] != 0.f ? 1.f : 0.f);
     u[i] = 1.f;
@@ -421,8 +433,14 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(Ipot
   for (int it = 0; it < a.iters; ++it) {
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {           // R1 = A * R
-      R[i][0] = __fmul2_rn(R[i][0], A[i][0]);
-      R[i][1] = __fmul2_rn(R[i][1], A[i][1]);
+      if constexpr (ASM) {
+        const float4 a4 = *reinterpret_cast<const float4*>(s_A + (size_t)(tr + i * RP) * MP + m0);
+        R[i][0] = __fmul2_rn(R[i][0], f2(a4.x, a4.y));
+        R[i][1] = __fmul2_rn(R[i][1], f2(a4.z, a4.w));
+      } else {
+        R[i][0] = __fmul2_rn(R[i][0], A[i][0]);
+        R[i][1] = __fmul2_rn(R[i][1], A[i][1]);
+      }
     }
     float z[RPT];
     for (int kk = 0; kk < a.k; ++kk) {
@@ -743,10 +761,10 @@ struct GradCfg {
   static constexpr bool F32 = DT == CE_F32;
   static constexpr int RS = kSlabBytes + (F32 ? 32 : 16);   // fp32: 40 words (== 8 mod 32); bf16: 36 words
   static constexpr int DCOLS = kSlabBytes / (F32 ? 4 : 2);  // columns per slab: 32 / 64
-  // W storage: fp32 [rows][MP+4] floats, or bf16 [rows][MP+8] + [MP][rows+8]
+  // W storage: fp32 [rows][MP+4] floats, or bf16 [rows][MP+8] (both orientations of the bf16 mma
+  // A operand are read from it: plain loads for W^t, ldmatrix.trans for W)
   __host__ __device__ static size_t w_bytes(int MP, int rows) {
-    return F32 ? sizeof(float) * (size_t)rows * (MP + 4)
-               : 2 * ((size_t)rows * (MP + 8) + (size_t)MP * (rows + 8));
+    return F32 ? sizeof(float) * (size_t)rows * (MP + 4) : 2 * (size_t)rows * (MP + 8);
   }
   __host__ __device__ static size_t smem_bytes(int MP, int rows) {
     return (size_t)kStages * (MP + rows) * RS + w_bytes(MP, rows) + sizeof(float) * (MP + rows) + 64;
@@ -793,10 +811,8 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
   // W, ax, ay of this CTA's rows (overlaps the first slabs' flight)
   constexpr int LDW = MP + 4;                 // fp32 W row stride (floats)
   constexpr int LDWB = MP + 8;                // bf16 W[n][m] row stride (elements)
-  const int LDWT = rows + 8;                  // bf16 W^t[m][n] row stride (elements)
   float* Ws = reinterpret_cast<float*>(wbase);
   __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(wbase);
-  __nv_bfloat16* Wt = Wb + (size_t)rows * LDWB;
   {
     const float* Wg = a.S + ((int64_t)b * a.N + row0) * MP;
     for (int idx = threadIdx.x; idx < rows * (MP / 4); idx += NT) {
@@ -808,10 +824,6 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
       } else {
         uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
         *reinterpret_cast<uint2*>(Wb + r * LDWB + c) = pk;
-        Wt[(c + 0) * LDWT + r] = __float2bfloat16_rn(v.x);
-        Wt[(c + 1) * LDWT + r] = __float2bfloat16_rn(v.y);
-        Wt[(c + 2) * LDWT + r] = __float2bfloat16_rn(v.z);
-        Wt[(c + 3) * LDWT + r] = __float2bfloat16_rn(v.w);
       }
     }
     for (int m = threadIdx.x; m < MP; m += NT) axs[m] = a.nx2[(int64_t)b * MP + m];
@@ -920,9 +932,12 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
           }
         } else {
           const uint8_t* ysb = stage + MP * RS;
+          // A = W[m][n] out of Wb[n][m]: four transposed 8x8 blocks (m lo/hi x k lo/hi)
+          const int blk = lane >> 3, br = lane & 7;
+          const __nv_bfloat16* wrow = Wb + (br + (blk >> 1) * 8) * LDWB + 16 * mi + (blk & 1) * 8;
           for (int ks = 0; ks < rows / 16; ++ks) {
-            const uint32_t* wr = reinterpret_cast<const uint32_t*>(Wt + (16 * mi + g) * LDWT + ks * 16) + t;
-            uint32_t af[4] = {wr[0], wr[8 * (LDWT / 2)], wr[4], wr[8 * (LDWT / 2) + 4]};
+            uint32_t af[4];
+            ldsm_x4_trans(af, wrow + ks * 16 * LDWB);
             uint32_t bf[2];
             ldsm_x2_trans(bf, ysb + (ks * 16 + (lane & 15)) * RS + j * 16);
             mma_bf16(acc, af, bf);
@@ -1179,13 +1194,20 @@ int launch_ipot_mp(const IpotArgs& a, int N, cudaStream_t st, bool* handled) {
   if (COND <= R) { ot_ipot_kernel<MP, R, G, ##__VA_ARGS__><<<(G == 32 ? (a.B + 7) / 8 : a.B), (G < 256 ? 256 : G), 0, st>>>(a); return CE_OK; }
   CE_IPOT_CASE(rptw, 2, 32) CE_IPOT_CASE(rptw, 4, 32) CE_IPOT_CASE(rptw, 7, 32) CE_IPOT_CASE(rptw, 10, 32)
   CE_IPOT_CASE(rpt256, 1, 256) CE_IPOT_CASE(rpt256, 2, 256) CE_IPOT_CASE(rpt256, 4, 256)
-  if (MP == 32 && variant == 1) { CE_IPOT_CASE(rpt256, 9, 256, 2, 0) }
+  if (MP == 32 && variant == 1) { CE_IPOT_CASE(rpt256, 9, 256, 1, 0) }
   if (MP == 32 && variant == 2) { CE_IPOT_CASE(rpt512, 5, 512, 1, 0) }
   if (MP == 32 && variant == 3) { CE_IPOT_CASE(rpt256, 9, 256, 2, 1) }
   if (MP == 32 && variant == 4) { CE_IPOT_CASE(rpt256, 9, 256, 1, 1) }
   if (MP == 32 && variant == 5) { CE_IPOT_CASE(rpt512, 5, 512, 1, 1) }
-  CE_IPOT_CASE(rpt256, 7, 256) CE_IPOT_CASE(rpt256, 9, 256) CE_IPOT_CASE(rpt256, 13, 256)
+  CE_IPOT_CASE(rpt256, 7, 256, 2, 0) CE_IPOT_CASE(rpt256, 9, 256, 2, 0) CE_IPOT_CASE(rpt256, 13, 256)
   CE_IPOT_CASE(rpt512, 10, 512) CE_IPOT_CASE(rpt512, 13, 512)
+  if (rpt512 <= 20) {   // kernel matrix in shared memory (64 x 577 and the like)
+    const size_t sm = sizeof(float) * (size_t)20 * (512 / TC) * MP;
+    auto kern = ot_ipot_kernel<MP, 20, 512, 1, 0, true>;
+    CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<a.B, 512, sm, st>>>(a);
+    return CE_OK;
+  }
 #undef CE_IPOT_CASE
   *handled = false;
   return CE_OK;
