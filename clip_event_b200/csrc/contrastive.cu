@@ -676,8 +676,8 @@ int plain_gemm_bn(const GemmOperand& A, const GemmOperand& B, int K, float* out,
   int splits = 1;
   if (tiles * 2 <= num_sms()) splits = std::max(1, std::min({num_sms() / tiles, kblk / 8, 16}));
   if (splits > 1 && !accumulate) CE_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)A.rows * ldo, st));
-  static const int acc_mode = getenv("CE_ACC_MODE") ? atoi(getenv("CE_ACC_MODE")) : 2;   // tuning aid
-  typename EpiStore<BN>::Params ep{out, ldo, rowscale, nullptr, ls, splits > 1 ? 1 : (accumulate ? acc_mode : 0), A.rows, B.rows};
+  // accumulate with red.add: a read-modify-write of the thread-per-row tile is 4x slower (measured)
+  typename EpiStore<BN>::Params ep{out, ldo, rowscale, nullptr, ls, (splits > 1 || accumulate) ? 1 : 0, A.rows, B.rows};
   return launch_gemm<TF, BN, EpiStore<BN>>(A, B, K, splits, ep, st);
 }
 template <bool TF>
