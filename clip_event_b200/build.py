@@ -36,6 +36,9 @@ def _stale() -> bool:
 
 def _compile(src: str) -> str:
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+    deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    if os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
+        return obj
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
     cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)

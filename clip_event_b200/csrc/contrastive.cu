@@ -40,6 +40,8 @@ struct EpiStats {
     float* lab_logit;   // [M] natural-log logit at that column, taken from the SAME accumulator so
                         //     that the tensor-core rounding cancels in (LSE - positive logit)
   };
+  static constexpr int kStageBytesPerWarp = 0;
+  uint8_t* stage;
   Params p;
   float kk, rinv_r, m2, l;
   int lab;
@@ -125,6 +127,11 @@ struct EpiGrad {
   // G = g' * t ; dls' += g' * v.   Here kr = s*log2e/|row|, cs = coef/(s*log2e), so that
   // g'*t = coef*softmax/(|row||col|) and sum(g*L) = s*log2e*ln2 * sum(g'*(v + lse)); the lse part
   // vanishes because a softmax-minus-one-hot row sums to zero.
+  // bf16: the warp's [32 rows x BN/2 columns] are staged in shared memory and written out with
+  // fully coalesced 16-byte stores (thread-per-row stores touch 32 half-filled sectors each).
+  static constexpr int kRowBytes = (BN / 2) * 2 + 16;
+  static constexpr int kStageBytesPerWarp = TF32X3 ? 0 : 32 * kRowBytes;
+  uint8_t* stage;
   float sl, kr, lse2r, cs, dls;
   int lab;
   __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et2) {
@@ -180,25 +187,26 @@ struct EpiGrad {
         }
       }
     }
-    if (!ok) return;
     if constexpr (!TF32X3) {
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.G0) + (int64_t)row * p.ldg + col0;
+      // lcol0 within this warp's column half: (lcol0 % (BN/2)) columns into the staged row
+      uint8_t* dst = stage + (threadIdx.x & 31) * kRowBytes + (lcol0 % (BN / 2)) * 2;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
-        if (col0 + i < p.ldg) {
-          uint4 pk;
-          __nv_bfloat162 t0 = __floats2bfloat162_rn(gs[i], gs[i + 1]);
-          __nv_bfloat162 t1 = __floats2bfloat162_rn(gs[i + 2], gs[i + 3]);
-          __nv_bfloat162 t2 = __floats2bfloat162_rn(gs[i + 4], gs[i + 5]);
-          __nv_bfloat162 t3 = __floats2bfloat162_rn(gs[i + 6], gs[i + 7]);
-          pk.x = *reinterpret_cast<uint32_t*>(&t0);
-          pk.y = *reinterpret_cast<uint32_t*>(&t1);
-          pk.z = *reinterpret_cast<uint32_t*>(&t2);
-          pk.w = *reinterpret_cast<uint32_t*>(&t3);
-          *reinterpret_cast<uint4*>(out + i) = pk;
-        }
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(gs[i], gs[i + 1]);
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(gs[i + 2], gs[i + 3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(gs[i + 4], gs[i + 5]);
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(gs[i + 6], gs[i + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0);
+        pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2);
+        pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(dst + i * 2) = pk;
       }
-    } else {
+      return;
+    }
+    if (!ok) return;
+    {
       float* o0 = reinterpret_cast<float*>(p.G0) + (int64_t)row * p.ldg + col0;
       float* o1 = reinterpret_cast<float*>(p.G1) + (int64_t)row * p.ldg + col0;
 #pragma unroll
@@ -216,11 +224,28 @@ struct EpiGrad {
       }
     }
   }
-  __device__ __forceinline__ void row_end(int, bool, int m_blk, int n_blk, int, float*, int et, int half) {
+  __device__ __forceinline__ void row_end(int row, bool, int m_blk, int n_blk, int, float*, int et, int half) {
     float v = warp_sum(dls * sl);
     if ((et & 31) == 0) {
       int tile = n_blk * ((p.M + kBM - 1) / kBM) + m_blk;
       p.dls_part[(int64_t)tile * 8 + half * 4 + (et >> 5)] = v;
+    }
+    if constexpr (!TF32X3) {
+      __syncwarp();
+      const int lane = et & 31;
+      const int row0 = row - lane;                               // first row of this warp
+      const int64_t colbase = (int64_t)n_blk * BN + half * (BN / 2);
+      constexpr int kPiecesPerRow = (BN / 2) / 8;                // 16-byte pieces (8 bf16) per staged row
+      __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(p.G0);
+#pragma unroll
+      for (int it = 0; it < kPiecesPerRow; ++it) {
+        const int piece = it * 32 + lane;
+        const int r = piece / kPiecesPerRow, c = piece % kPiecesPerRow;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + r * kRowBytes + c * 16);
+        if (row0 + r < p.M && colbase + c * 8 < p.ldg)
+          *reinterpret_cast<uint4*>(G + (int64_t)(row0 + r) * p.ldg + colbase + c * 8) = val;
+      }
+      __syncwarp();
     }
   }
 };
@@ -236,6 +261,8 @@ struct EpiStore {
     int atomic;                // 1: accumulate with red.add (split-K); 2: exclusive tile, out += v
     int M, N;
   };
+  static constexpr int kStageBytesPerWarp = 0;
+  uint8_t* stage;
   Params p;
   float rs;
   __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et2) {

@@ -35,7 +35,7 @@ struct GemmShape {
   int a_mn, b_mn;          // operand majorness: 0 = K-major, 1 = MN-major
 };
 
-template <bool TF32X3, int BN>
+template <bool TF32X3, int BN, int EPI_STAGE = 0>   // EPI_STAGE: bytes of epilogue staging smem
 struct GemmCfg {
   static constexpr int kElemBytes = TF32X3 ? 4 : 2;
   static constexpr int kBK = kSwizzleBytes / kElemBytes;     // elements of K per stage: 32 / 64
@@ -44,11 +44,13 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kSwizzleBytes;        // one A part per stage
   static constexpr int kBBytes = BN * kSwizzleBytes;
   static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
+  static constexpr int kBudget = 216 * 1024 - EPI_STAGE;
+  static constexpr int kStages = kBudget / kStageBytes > 6 ? 6 : kBudget / kStageBytes;
+  static constexpr int kEpiStageBytes = EPI_STAGE;
   static constexpr int kTmemCols = 2 * BN;                   // double-buffered accumulator
   static constexpr int kEpiFloats = 4 * BN;                  // per-tile column data for the epilogue
   static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes +
-                                       sizeof(float) * kEpiFloats + 256 /*barriers*/;
+                                       sizeof(float) * kEpiFloats + 256 /*barriers*/ + EPI_STAGE;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns");
 };
@@ -69,7 +71,7 @@ struct TmapSet {
 template <bool TF32X3, int BN, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const typename Epi::Params ep) {
-  using Cfg = GemmCfg<TF32X3, BN>;
+  using Cfg = GemmCfg<TF32X3, BN, Epi::kStageBytesPerWarp * 8>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -80,6 +82,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;   // [8 warps][kStageBytesPerWarp]
 
   const int warp = warp_id(), lane = lane_id();
   const int num_tiles = gs.num_m_blk * gs.num_n_blk;
@@ -187,7 +190,9 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
-    Epi epi{ep};
+    Epi epi;
+    epi.p = ep;
+    epi.stage = epi_stage + (warp - 4) * Epi::kStageBytesPerWarp;
     const int q = (warp - 4) & 3;       // TMEM lane quadrant
     const int half = (warp - 4) >> 2;   // column half of the tile
     const int et = q * 32 + lane;       // 0..127 = row inside the tile
@@ -267,7 +272,7 @@ int build_tmaps(TmapSet* tm, GemmShape* gs, const GemmOperand& A, const GemmOper
 template <bool TF32X3, int BN, class Epi>
 int launch_gemm(const GemmOperand& A, const GemmOperand& B, int K, int k_splits,
                 const typename Epi::Params& ep, cudaStream_t st, int* items_out = nullptr) {
-  using Cfg = GemmCfg<TF32X3, BN>;
+  using Cfg = GemmCfg<TF32X3, BN, Epi::kStageBytesPerWarp * 8>;
   TmapSet tm;
   GemmShape gs;
   CE_TRY((build_tmaps<TF32X3, BN>(&tm, &gs, A, B, K, k_splits)));
