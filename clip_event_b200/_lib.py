@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libclip_event_b200.so")
 
 CE_F32, CE_BF16 = 0, 1
 CE_MASK_NUM_I64, CE_MASK_PAD_U8 = 0, 1
+CE_IMG_CE_OVERBATCH, CE_IMG_CE_INSTANCE, CE_IMG_BCE_INSTANCE = 0, 1, 2
 
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
@@ -23,12 +24,12 @@ SIGNATURES = {
     "ce_last_error": (C.c_char_p, []),
     "ce_device_check": (_i, []),
     "ce_contrastive_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "ce_contrastive_fwd_partial": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ce_contrastive_fwd_partial": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _i, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
     "ce_contrastive_fwd_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
-    "ce_contrastive_bwd_partial": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ce_contrastive_bwd_partial": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _i, _i64, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ce_contrastive_bwd_finish": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
-    "ce_contrastive_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
-    "ce_contrastive_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ce_contrastive_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ce_contrastive_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ce_similarity_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ce_similarity_logits": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "ce_ot_workspace_bytes": (_sz, [_i, _i, _i, _i]),

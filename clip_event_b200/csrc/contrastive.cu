@@ -380,7 +380,7 @@ __global__ void label_prep_kernel(const int64_t* labels_i, const int64_t* labels
                                   int* lab_local, float* lab_logit_i, int* lab_t, float* lab_logit_t) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < R) {
-    int64_t lab = labels_i[i] - col_offset;
+    int64_t lab = labels_i != nullptr ? labels_i[i] - col_offset : -1;
     lab_local[i] = (lab >= 0 && lab < C) ? (int)lab : -1;
     lab_logit_i[i] = 0.f;
   } else if (i < R + P) {
@@ -389,6 +389,102 @@ __global__ void label_prep_kernel(const int64_t* labels_i, const int64_t* labels
     lab_t[p] = (row >= 0 && row < R) ? (int)row : -1;
     lab_logit_t[p] = 0.f;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Over-instance image side (constrastive_overbatch = False, model_clip.py:509-520): every image is
+// scored against its own T descriptions only -- B*T dot products, no GEMM.  One warp per image.
+//   mode 1: 'ce'  loss_i = mean_b ( LSE_t L[b,:] - L[b, lab[b]] )           labels int64 [b] in [0,T)
+//   mode 2: 'bce' loss_i = mean_{b,t} ( softplus(L) - y L )                   labels fp32  [b, T]
+// ------------------------------------------------------------------------------------------
+struct InstArgs {
+  const void* img;        // [R, D] all (gathered) images
+  const void* txt;        // [b*T, D] local descriptions
+  const float* logit_scale;
+  const void* labels;
+  const float *rinv_i, *rinv_t;
+  int b, T, D, mode;
+  int64_t row_offset;     // global row of local image 0
+  float* logits;          // [b, T] fp32 (kept for the backward)
+  float4* row_part;       // [R] forward: (0, 1, -item, 0) on local rows, (-inf, 0, 0, 0) elsewhere
+  int R;
+  // backward
+  const float* g;         // dL/dloss_i
+  float inv_count;        // 1 / B_total
+  float* dimg_hat;        // [R, D] fp32, written (local rows) -- gradient w.r.t. the normalised image
+  float* dtxt_hat;        // [b*T, D] fp32, written
+  float* dls_part;        // [b]
+};
+
+template <int DT>
+__global__ void instance_fwd_kernel(InstArgs a) {
+  int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wi >= a.R) return;
+  int64_t lb = wi - a.row_offset;
+  if (lb < 0 || lb >= a.b) {
+    if (lane == 0) a.row_part[wi] = make_float4(-INFINITY, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float s = expf(__ldg(a.logit_scale));
+  float m = -INFINITY, item = 0.f, picked = 0.f;
+  const int64_t lab = a.mode == 1 ? reinterpret_cast<const int64_t*>(a.labels)[lb] : 0;
+  for (int t = 0; t < a.T; ++t) {
+    int64_t c = lb * a.T + t;
+    float l = s * a.rinv_i[wi] * a.rinv_t[c] * warp_dot<DT>(a.img, wi, a.txt, c, a.D);
+    if (lane == 0) a.logits[c] = l;
+    if (a.mode == 1) {
+      m = fmaxf(m, l);
+      if (t == lab) picked = l;
+    } else {
+      float y = reinterpret_cast<const float*>(a.labels)[c];
+      item += fmaxf(l, 0.f) + log1pf(expf(-fabsf(l))) - y * l;      // softplus(l) - y l
+    }
+  }
+  if (a.mode == 1) {
+    float se = 0.f;
+    __syncwarp();
+    for (int t = 0; t < a.T; ++t) se += expf(a.logits[lb * a.T + t] - m);
+    item = m + logf(se) - picked;
+  } else {
+    item /= (float)a.T;
+  }
+  if (lane == 0) a.row_part[wi] = make_float4(0.f, 1.f, -item, 0.f);
+}
+
+template <int DT>
+__global__ void instance_bwd_kernel(InstArgs a) {
+  using T_ = typename In<DT>::type;
+  int lb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (lb >= a.b) return;
+  const int64_t row = a.row_offset + lb;
+  const float s = expf(__ldg(a.logit_scale));
+  const float coef = __ldg(a.g) * a.inv_count;
+  float m = -INFINITY, se = 0.f;
+  if (a.mode == 1) {
+    for (int t = 0; t < a.T; ++t) m = fmaxf(m, a.logits[(int64_t)lb * a.T + t]);
+    for (int t = 0; t < a.T; ++t) se += expf(a.logits[(int64_t)lb * a.T + t] - m);
+  }
+  const int64_t lab = a.mode == 1 ? reinterpret_cast<const int64_t*>(a.labels)[lb] : 0;
+  const T_* xi = reinterpret_cast<const T_*>(a.img) + row * a.D;
+  const float ri = a.rinv_i[row];
+  float dls = 0.f;
+  // d I^ = s * sum_t dL_t T^_t ;  d T^_t = s * dL_t I^
+  for (int d = lane; d < a.D; d += 32) a.dimg_hat[row * a.D + d] = 0.f;
+  for (int t = 0; t < a.T; ++t) {
+    const int64_t c = (int64_t)lb * a.T + t;
+    const float l = a.logits[c];
+    float dl;
+    if (a.mode == 1) dl = coef * (expf(l - m) / se - (t == lab ? 1.f : 0.f));
+    else dl = coef / (float)a.T * (1.f / (1.f + expf(-l)) - reinterpret_cast<const float*>(a.labels)[c]);
+    dls += dl * l;
+    const T_* xt = reinterpret_cast<const T_*>(a.txt) + c * a.D;
+    const float rt = a.rinv_t[c];
+    for (int d = lane; d < a.D; d += 32) {
+      a.dimg_hat[row * a.D + d] += s * dl * rt * In<DT>::ld(xt + d);
+      a.dtxt_hat[c * a.D + d] = s * dl * ri * In<DT>::ld(xi + d);
+    }
+  }
+  if (lane == 0) a.dls_part[lb] = dls / kLn2;   // sum_dls_kernel multiplies by ln2
 }
 
 struct ItemArgs {
@@ -405,6 +501,7 @@ struct ItemArgs {
   const float* lab_logit_t;  // [P]
   float* lse2_col;    // [P]
   float* item_t;      // [P]  colLSE - positive logit
+  int image_side;     // 0: the image-side rows were produced elsewhere (over-instance mode)
 };
 
 // One warp per item: rows 0..R-1 (image side), then P text-side items.
@@ -413,6 +510,7 @@ __global__ void fwd_items_kernel(ItemArgs a) {
   int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (it < a.R) {
+    if (!a.image_side) return;
     int r = it;
     float m = -INFINITY, l = 0.f;
     for (int j = lane; j < a.nblk_i; j += 32) {
@@ -577,7 +675,7 @@ struct CtrWs {
   void *img_p[2], *txt_p[2], *pos_p[2];
   void* G[2];      // image-side gradient matrix [R, ldg]
   void* Gt[2];     // text-side  gradient matrix [P, ldgt]
-  float *dtxt_hat, *dimg_hat, *dpos_hat;
+  float *dtxt_hat, *dimg_hat, *dpos_hat, *logits_bt;
   int64_t ldg, ldgt;
   int nblk_i, nblk_t, tiles_g, tiles_gt;
   size_t bytes;
@@ -604,7 +702,8 @@ CtrWs carve(void* base, int R, int C, int P, int D, int dtype) {
   w.part_t = cv.take<float2>((size_t)P * w.nblk_t * 2);
   w.row_part = cv.take<float4>(R);
   w.sums = cv.take<float>(4);
-  w.dls_part = cv.take<float>((size_t)(w.tiles_g + w.tiles_gt) * 8);
+  w.dls_part = cv.take<float>((size_t)(w.tiles_g + w.tiles_gt) * 8 + (size_t)C);
+  w.logits_bt = cv.take<float>((size_t)C);
   if (dtype == CE_F32) {
     for (int i = 0; i < 2; ++i) {
       w.img_p[i] = cv.take<float>((size_t)R * D);
@@ -658,11 +757,13 @@ GemmOperand operand(const void* raw, void* const* parts, int rows, int64_t ld, i
 }
 
 template <int DT>
-int fwd_partial_impl(const void* img, const void* txt, const float* ls, const int64_t* labels_i,
+int fwd_partial_impl(const void* img, const void* txt, const float* ls, const void* labels_i_v,
                      const int64_t* labels_t, const int64_t* index_pos, int R, int C, int P, int D,
-                     int64_t col_offset, float* row_part, float* sums, CtrWs& w, cudaStream_t st) {
+                     int64_t col_offset, int mode, int T, int64_t row_offset, float* row_part,
+                     float* sums, CtrWs& w, cudaStream_t st) {
   constexpr bool TF = DT == CE_F32;
   constexpr int BN = s_bn<DT>();
+  const int64_t* labels_i = mode == 0 ? reinterpret_cast<const int64_t*>(labels_i_v) : nullptr;
   CE_TRY(run_prep<DT>(img, nullptr, R, D, w.rinv_i, w.norm_i, TF ? w.img_p[0] : nullptr, w.img_p[1], st));
   CE_TRY(run_prep<DT>(txt, nullptr, C, D, w.rinv_t, w.norm_t, TF ? w.txt_p[0] : nullptr, w.txt_p[1], st));
   CE_TRY(run_prep<DT>(txt, index_pos, P, D, w.rinv_p, nullptr, w.pos_p[0], w.pos_p[1], st));
@@ -672,9 +773,16 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const in
   GemmOperand oi = operand<DT>(img, w.img_p, R, D, 0);
   GemmOperand ot = operand<DT>(txt, w.txt_p, C, D, 0);
   GemmOperand op = operand<DT>(w.pos_p[0], w.pos_p, P, D, 0);
-  {
+  if (mode == 0) {
     typename EpiStats<BN>::Params ep{w.rinv_i, w.rinv_t, ls, w.part_i, R, C, w.nblk_i, w.lab_local, w.lab_logit_i};
     CE_TRY((launch_gemm<TF, BN, EpiStats<BN>>(oi, ot, D, 1, ep, st)));
+  } else {
+    InstArgs ia{};
+    ia.img = img; ia.txt = txt; ia.logit_scale = ls; ia.labels = labels_i_v; ia.rinv_i = w.rinv_i;
+    ia.rinv_t = w.rinv_t; ia.b = C / T; ia.T = T; ia.D = D; ia.mode = mode; ia.row_offset = row_offset;
+    ia.logits = w.logits_bt; ia.row_part = reinterpret_cast<float4*>(row_part); ia.R = R;
+    instance_fwd_kernel<DT><<<(R * 32 + 255) / 256, 256, 0, st>>>(ia);
+    CE_LAUNCH_CHECK();
   }
   {
     typename EpiStats<BN>::Params ep{w.rinv_p, w.rinv_i, ls, w.part_t, P, R, w.nblk_t, w.lab_t, w.lab_logit_t};
@@ -682,7 +790,7 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const in
   }
   ItemArgs ia{img, txt, ls, labels_i, labels_t, index_pos, w.rinv_i, w.rinv_t, w.part_i, 2 * w.nblk_i,
               w.part_t, 2 * w.nblk_t, R, C, P, D, col_offset, reinterpret_cast<float4*>(row_part),
-              w.lab_logit_i, w.lab_logit_t, w.lse2_col, w.item_t};
+              w.lab_logit_i, w.lab_logit_t, w.lse2_col, w.item_t, mode == 0 ? 1 : 0};
   int blocks = ((R + P) * 32 + 255) / 256;
   fwd_items_kernel<DT><<<blocks, 256, 0, st>>>(ia);
   CE_LAUNCH_CHECK();
@@ -721,10 +829,11 @@ int plain_gemm(const GemmOperand& A, const GemmOperand& B, int K, float* out, in
 }
 
 template <int DT>
-int bwd_partial_impl(const void* img, const void* txt, const float* ls, const int64_t* labels_t,
-                     const int64_t* index_pos, int R, int C, int P, int D, const float* g_i,
-                     const float* g_t, int R_total, int P_total, void* dtxt, float* dimg_hat_part,
-                     float* dls_out, CtrWs& w, cudaStream_t st) {
+int bwd_partial_impl(const void* img, const void* txt, const float* ls, const void* labels_i_v,
+                     const int64_t* labels_t, const int64_t* index_pos, int R, int C, int P, int D,
+                     int mode, int T, int64_t row_offset, const float* g_i, const float* g_t,
+                     int R_total, int P_total, void* dtxt, float* dimg_hat_part, float* dls_out,
+                     CtrWs& w, cudaStream_t st) {
   (void)labels_t;
   constexpr bool TF = DT == CE_F32;
   constexpr int BN = s_bn<DT>();
@@ -735,12 +844,24 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const in
   GemmOperand oi = operand<DT>(img, w.img_p, R, D, 0);
   GemmOperand ot = operand<DT>(txt, w.txt_p, C, D, 0);
   GemmOperand op = operand<DT>(w.pos_p[0], w.pos_p, P, D, 0);
-  {  // image side: rows = images, columns = local descriptions
+  const int n_dls = (w.tiles_g + w.tiles_gt) * 8 + (mode == 0 ? 0 : C / T);
+  if (mode == 0) {  // image side: rows = images, columns = local descriptions
     typename EpiGrad<BN, TF>::Params ep{};
     ep.rinv_row = w.rinv_i; ep.rinv_col = w.rinv_t; ep.logit_scale = ls; ep.lse2_row = w.lse2_row;
     ep.lab_row = w.lab_local; ep.g = g_i; ep.inv_count = 1.f / (float)R_total;
     ep.G0 = w.G[0]; ep.G1 = w.G[1]; ep.ldg = w.ldg; ep.dls_part = w.dls_part; ep.M = R; ep.N = C;
     CE_TRY((launch_gemm<TF, BN, EpiGrad<BN, TF>>(oi, ot, D, 1, ep, st)));
+  } else {          // over-instance image side: direct kernel, writes d I^ (local rows) and d T^
+    CE_CUDA_TRY(cudaMemsetAsync(w.dls_part, 0, sizeof(float) * (size_t)w.tiles_g * 8, st));
+    CE_CUDA_TRY(cudaMemsetAsync(dimg_hat_part, 0, sizeof(float) * (size_t)R * D, st));
+    InstArgs ia{};
+    ia.img = img; ia.txt = txt; ia.logit_scale = ls; ia.labels = labels_i_v; ia.rinv_i = w.rinv_i;
+    ia.rinv_t = w.rinv_t; ia.b = C / T; ia.T = T; ia.D = D; ia.mode = mode; ia.row_offset = row_offset;
+    ia.logits = w.logits_bt; ia.R = R; ia.g = g_i; ia.inv_count = 1.f / (float)R_total;
+    ia.dimg_hat = dimg_hat_part; ia.dtxt_hat = w.dtxt_hat;
+    ia.dls_part = w.dls_part + (size_t)(w.tiles_g + w.tiles_gt) * 8;
+    instance_bwd_kernel<DT><<<((C / T) * 32 + 255) / 256, 256, 0, st>>>(ia);
+    CE_LAUNCH_CHECK();
   }
   {  // text side: rows = local positive descriptions, columns = images
     typename EpiGrad<BN, TF>::Params ep{};
@@ -750,16 +871,18 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const in
     ep.M = P; ep.N = R;
     CE_TRY((launch_gemm<TF, BN, EpiGrad<BN, TF>>(op, oi, D, 1, ep, st)));
   }
-  sum_dls_kernel<<<1, 1024, 0, st>>>(w.dls_part, (w.tiles_g + w.tiles_gt) * 8, dls_out);
+  sum_dls_kernel<<<1, 1024, 0, st>>>(w.dls_part, n_dls, dls_out);
   CE_LAUNCH_CHECK();
   GemmOperand tB = operand<DT>(txt, w.txt_p, D, D, 1);          // [K = C, N = D]
   GemmOperand iB = operand<DT>(img, w.img_p, D, D, 1);          // [K = R, N = D]
   GemmOperand pB = operand<DT>(w.pos_p[0], w.pos_p, D, D, 1);   // [K = P, N = D]
   // d I^ (partial over the local columns) = s |i| (G txt + Gt^t pos)
-  CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, R, w.ldg, 0), tB, C, dimg_hat_part, D, w.norm_i, ls, false, st)));
+  if (mode == 0)
+    CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, R, w.ldg, 0), tB, C, dimg_hat_part, D, w.norm_i, ls, false, st)));
   CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, R, w.ldgt, 1), pB, P, dimg_hat_part, D, w.norm_i, ls, true, st)));
   // d T^ = s |t| G^t img  (+ s |t_pos| Gt img on the positive rows, added by the row kernel)
-  CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, C, w.ldg, 1), iB, R, w.dtxt_hat, D, w.norm_t, ls, false, st)));
+  if (mode == 0)
+    CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, C, w.ldg, 1), iB, R, w.dtxt_hat, D, w.norm_t, ls, false, st)));
   CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, P, w.ldgt, 0), iB, R, w.dpos_hat, D, nullptr, ls, false, st)));
   // dpos_hat rows still miss the |t_pos| factor: norm_t[index_pos[p]]; fold it in the row kernel via
   // the same normalisation (x^ . d and the final 1/|x| are linear in d) -- see normalize_bwd_kernel.
@@ -780,18 +903,29 @@ extern "C" size_t ce_contrastive_workspace_bytes(int R, int C, int P, int D, int
   return carve(nullptr, R, C, P, D, dtype).bytes;
 }
 
+static int check_mode(int image_loss, int T, int C, int64_t row_offset, int R) {
+  if (image_loss < 0 || image_loss > 2) return fail(CE_ERR_ARG, "contrastive: unknown image_loss %d", image_loss);
+  if (image_loss != 0) {
+    if (T < 1 || C % T != 0) return fail(CE_ERR_SHAPE, "contrastive: over-instance mode needs C (%d) divisible by T (%d)", C, T);
+    if (row_offset < 0 || row_offset + C / T > R) return fail(CE_ERR_SHAPE, "contrastive: local images fall outside the gathered rows");
+  }
+  return CE_OK;
+}
+
 extern "C" int ce_contrastive_fwd_partial(const void* img, const void* txt, const float* logit_scale,
-                                          const int64_t* labels_i, const int64_t* labels_t,
+                                          const void* labels_i, const int64_t* labels_t,
                                           const int64_t* index_pos, int R, int C, int P, int D,
-                                          int64_t col_offset, int dtype, float* row_part, float* sums,
+                                          int64_t col_offset, int image_loss, int T, int64_t row_offset,
+                                          int dtype, float* row_part, float* sums,
                                           void* workspace, size_t workspace_bytes, ce_stream_t stream) {
   CE_TRY(check_device());
   CE_TRY(check_common(R, C, P, D, dtype, img, txt));
+  CE_TRY(check_mode(image_loss, T, C, row_offset, R));
   CtrWs w = carve(workspace, R, C, P, D, dtype);
   if (workspace_bytes < w.bytes) return fail(CE_ERR_WORKSPACE, "contrastive: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == CE_F32) return fwd_partial_impl<CE_F32>(img, txt, logit_scale, labels_i, labels_t, index_pos, R, C, P, D, col_offset, row_part, sums, w, st);
-  return fwd_partial_impl<CE_BF16>(img, txt, logit_scale, labels_i, labels_t, index_pos, R, C, P, D, col_offset, row_part, sums, w, st);
+  if (dtype == CE_F32) return fwd_partial_impl<CE_F32>(img, txt, logit_scale, labels_i, labels_t, index_pos, R, C, P, D, col_offset, image_loss, T, row_offset, row_part, sums, w, st);
+  return fwd_partial_impl<CE_BF16>(img, txt, logit_scale, labels_i, labels_t, index_pos, R, C, P, D, col_offset, image_loss, T, row_offset, row_part, sums, w, st);
 }
 
 extern "C" int ce_contrastive_fwd_finish(const float* row_part_all, const float* sums_all, int world,
@@ -809,22 +943,24 @@ extern "C" int ce_contrastive_fwd_finish(const float* row_part_all, const float*
 }
 
 extern "C" int ce_contrastive_bwd_partial(const void* img, const void* txt, const float* logit_scale,
-                                          const int64_t* labels_i, const int64_t* labels_t,
+                                          const void* labels_i, const int64_t* labels_t,
                                           const int64_t* index_pos, int R, int C, int P, int D,
-                                          int64_t col_offset, int dtype, const float* g_i,
+                                          int64_t col_offset, int image_loss, int T, int64_t row_offset,
+                                          int dtype, const float* g_i,
                                           const float* g_t, int R_total, int P_total, void* dtxt,
                                           float* dimg_hat_part, float* dlogit_scale_part,
                                           void* workspace, size_t workspace_bytes, ce_stream_t stream) {
-  (void)labels_i; (void)col_offset;  // the local label columns were resolved by the forward
+  (void)col_offset;  // the local label columns were resolved by the forward
   CE_TRY(check_device());
   CE_TRY(check_common(R, C, P, D, dtype, img, txt));
+  CE_TRY(check_mode(image_loss, T, C, row_offset, R));
   if (((uintptr_t)dtxt | (uintptr_t)dimg_hat_part) & 15) return fail(CE_ERR_ALIGN, "contrastive: gradient buffers must be 16-byte aligned");
   if (R_total < 1 || P_total < 1) return fail(CE_ERR_ARG, "contrastive: R_total and P_total must be >= 1");
   CtrWs w = carve(workspace, R, C, P, D, dtype);
   if (workspace_bytes < w.bytes) return fail(CE_ERR_WORKSPACE, "contrastive: workspace too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == CE_F32) return bwd_partial_impl<CE_F32>(img, txt, logit_scale, labels_t, index_pos, R, C, P, D, g_i, g_t, R_total, P_total, dtxt, dimg_hat_part, dlogit_scale_part, w, st);
-  return bwd_partial_impl<CE_BF16>(img, txt, logit_scale, labels_t, index_pos, R, C, P, D, g_i, g_t, R_total, P_total, dtxt, dimg_hat_part, dlogit_scale_part, w, st);
+  if (dtype == CE_F32) return bwd_partial_impl<CE_F32>(img, txt, logit_scale, labels_i, labels_t, index_pos, R, C, P, D, image_loss, T, row_offset, g_i, g_t, R_total, P_total, dtxt, dimg_hat_part, dlogit_scale_part, w, st);
+  return bwd_partial_impl<CE_BF16>(img, txt, logit_scale, labels_i, labels_t, index_pos, R, C, P, D, image_loss, T, row_offset, g_i, g_t, R_total, P_total, dtxt, dimg_hat_part, dlogit_scale_part, w, st);
 }
 
 extern "C" int ce_contrastive_bwd_finish(const void* img_rows, const float* dimg_hat_rows, int rows,
@@ -842,8 +978,9 @@ extern "C" int ce_contrastive_bwd_finish(const void* img_rows, const float* dimg
 }
 
 extern "C" int ce_contrastive_fwd(const void* img, const void* txt, const float* logit_scale,
-                                  const int64_t* labels_i, const int64_t* labels_t,
-                                  const int64_t* index_pos, int B, int BT, int P, int D, int dtype,
+                                  const void* labels_i, const int64_t* labels_t,
+                                  const int64_t* index_pos, int B, int BT, int P, int D, int image_loss,
+                                  int dtype,
                                   float* loss_i, float* loss_t, void* workspace,
                                   size_t workspace_bytes, ce_stream_t stream) {
   CE_TRY(check_device());
@@ -851,15 +988,17 @@ extern "C" int ce_contrastive_fwd(const void* img, const void* txt, const float*
   CtrWs w = carve(workspace, B, BT, P, D, dtype);
   if (workspace_bytes < w.bytes) return fail(CE_ERR_WORKSPACE, "contrastive: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
   CE_TRY(ce_contrastive_fwd_partial(img, txt, logit_scale, labels_i, labels_t, index_pos, B, BT, P, D, 0,
-                                    dtype, reinterpret_cast<float*>(w.row_part), w.sums, workspace,
+                                    image_loss, B > 0 ? BT / B : 1, 0, dtype,
+                                    reinterpret_cast<float*>(w.row_part), w.sums, workspace,
                                     workspace_bytes, stream));
   return ce_contrastive_fwd_finish(reinterpret_cast<const float*>(w.row_part), w.sums, 1, B, BT, P, D,
                                    dtype, loss_i, loss_t, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ce_contrastive_bwd(const void* img, const void* txt, const float* logit_scale,
-                                  const int64_t* labels_i, const int64_t* labels_t,
-                                  const int64_t* index_pos, int B, int BT, int P, int D, int dtype,
+                                  const void* labels_i, const int64_t* labels_t,
+                                  const int64_t* index_pos, int B, int BT, int P, int D, int image_loss,
+                                  int dtype,
                                   const float* g_i, const float* g_t, void* dimg, void* dtxt,
                                   float* dlogit_scale, void* workspace, size_t workspace_bytes,
                                   ce_stream_t stream) {
@@ -868,8 +1007,8 @@ extern "C" int ce_contrastive_bwd(const void* img, const void* txt, const float*
   CtrWs w = carve(workspace, B, BT, P, D, dtype);
   if (workspace_bytes < w.bytes) return fail(CE_ERR_WORKSPACE, "contrastive: workspace too small");
   CE_TRY(ce_contrastive_bwd_partial(img, txt, logit_scale, labels_i, labels_t, index_pos, B, BT, P, D, 0,
-                                    dtype, g_i, g_t, B, P, dtxt, w.dimg_hat, dlogit_scale, workspace,
-                                    workspace_bytes, stream));
+                                    image_loss, B > 0 ? BT / B : 1, 0, dtype, g_i, g_t, B, P, dtxt,
+                                    w.dimg_hat, dlogit_scale, workspace, workspace_bytes, stream));
   return ce_contrastive_bwd_finish(img, w.dimg_hat, B, D, dtype, dimg, stream);
 }
 

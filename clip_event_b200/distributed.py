@@ -47,7 +47,8 @@ class CudaBackend:
         sums = torch.empty(4, dtype=torch.float32, device=img_all.device)
         L.check(self.lib.ce_contrastive_fwd_partial(
             img_all.data_ptr(), txt.data_ptr(), ls.data_ptr(), labels_i_all.data_ptr(), labels_t.data_ptr(),
-            index_pos.data_ptr(), R, C, P, D, int(col_offset), dt, row_part.data_ptr(), sums.data_ptr(),
+            index_pos.data_ptr(), R, C, P, D, int(col_offset), L.CE_IMG_CE_OVERBATCH, 1, 0, dt,
+            row_part.data_ptr(), sums.data_ptr(),
             ws.data_ptr(), nbytes, L.stream_ptr()), "contrastive fwd_partial")
         return row_part, sums, (ws, R, C, P, D, dt)
 
@@ -67,7 +68,8 @@ class CudaBackend:
         dls = torch.empty(1, dtype=torch.float32, device=txt.device)
         L.check(self.lib.ce_contrastive_bwd_partial(
             img_all.data_ptr(), txt.data_ptr(), ls.data_ptr(), labels_i_all.data_ptr(), labels_t.data_ptr(),
-            index_pos.data_ptr(), R, C, P, D, int(col_offset), dt, g_i.data_ptr(), g_t.data_ptr(),
+            index_pos.data_ptr(), R, C, P, D, int(col_offset), L.CE_IMG_CE_OVERBATCH, 1, 0, dt,
+            g_i.data_ptr(), g_t.data_ptr(),
             int(R_total), int(P_total), dtxt.data_ptr(), dimg_hat.data_ptr(), dls.data_ptr(),
             ws.data_ptr(), ws.numel(), L.stream_ptr()), "contrastive bwd_partial")
         return dtxt, dimg_hat, dls

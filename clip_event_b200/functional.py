@@ -24,11 +24,20 @@ def _scalar_f32(t: torch.Tensor, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # similarity + InfoNCE (over batch)
 # --------------------------------------------------------------------------------------------
+IMAGE_LOSS = {"ce_overbatch": L.CE_IMG_CE_OVERBATCH, "ce_instance": L.CE_IMG_CE_INSTANCE,
+              "bce_instance": L.CE_IMG_BCE_INSTANCE}
+
+
 class _ContrastiveOverBatch(torch.autograd.Function):
-    """(image_features, text_features, logit_scale) -> (loss_i, loss_t); model_clip.py:496-508,633-662."""
+    """(image_features, text_features, logit_scale) -> (loss_i, loss_t); model_clip.py:496-520,633-662.
+
+    ``image_loss`` selects the image side: 'ce_overbatch' (labels int64 [B] = positive column),
+    'ce_instance' (labels int64 [B] in [0,T)) or 'bce_instance' (labels float [B,T]).  The text
+    side is always the over-batch cross-entropy of the ``index_pos`` rows.
+    """
 
     @staticmethod
-    def forward(ctx, img, txt, logit_scale, labels_i, labels_t, index_pos):
+    def forward(ctx, img, txt, logit_scale, labels_i, labels_t, index_pos, image_loss="ce_overbatch"):
         L.require_cuda(img, txt, logit_scale)
         if img.dtype != txt.dtype:
             raise RuntimeError("image_features and text_features must share a dtype")
@@ -38,20 +47,29 @@ class _ContrastiveOverBatch(torch.autograd.Function):
         dev = img.device
         img_c, txt_c = img.detach().contiguous(), txt.detach().contiguous()
         ls = _scalar_f32(logit_scale, dev)
-        labels_i, labels_t, index_pos = _i64(labels_i, dev), _i64(labels_t, dev), _i64(index_pos, dev)
+        mode = IMAGE_LOSS[image_loss]
+        labels_t, index_pos = _i64(labels_t, dev), _i64(index_pos, dev)
         B, D = img_c.shape
         BT, P = txt_c.shape[0], index_pos.numel()
-        if labels_i.numel() != B:
-            raise RuntimeError("labels_per_image must have one entry per image")
+        if mode == L.CE_IMG_BCE_INSTANCE:
+            labels_i = labels_i.to(device=dev, dtype=torch.float32).contiguous()
+            if B == 0 or BT % B or labels_i.numel() != BT:
+                raise RuntimeError("'bce' labels_per_image must be [B, T] with B*T descriptions")
+        else:
+            labels_i = _i64(labels_i, dev)
+            if labels_i.numel() != B:
+                raise RuntimeError("labels_per_image must have one entry per image")
+            if mode == L.CE_IMG_CE_INSTANCE and (B == 0 or BT % B):
+                raise RuntimeError("over-instance logits need B*T descriptions")
         lib = L.load()
         nbytes = lib.ce_contrastive_workspace_bytes(B, BT, P, D, dt)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         out = torch.empty(2, dtype=torch.float32, device=dev)
         L.check(lib.ce_contrastive_fwd(L.ptr(img_c), L.ptr(txt_c), L.ptr(ls), L.ptr(labels_i), L.ptr(labels_t),
-                                       L.ptr(index_pos), B, BT, P, D, dt, out.data_ptr(), out.data_ptr() + 4,
+                                       L.ptr(index_pos), B, BT, P, D, mode, dt, out.data_ptr(), out.data_ptr() + 4,
                                        ws.data_ptr(), nbytes, L.stream_ptr()), "contrastive forward")
         ctx.save_for_backward(img_c, txt_c, ls, labels_i, labels_t, index_pos, ws)
-        ctx.dims = (B, BT, P, D, dt)
+        ctx.dims = (B, BT, P, D, dt, mode)
         ctx.ls_dtype = logit_scale.dtype
         ctx.ls_shape = logit_scale.shape
         return out[0], out[1]
@@ -59,7 +77,7 @@ class _ContrastiveOverBatch(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_i, g_t):
         img, txt, ls, labels_i, labels_t, index_pos, ws = ctx.saved_tensors
-        B, BT, P, D, dt = ctx.dims
+        B, BT, P, D, dt, mode = ctx.dims
         dev = img.device
         zero = torch.zeros(1, dtype=torch.float32, device=dev)
         gi = zero if g_i is None else _scalar_f32(g_i, dev)
@@ -68,17 +86,27 @@ class _ContrastiveOverBatch(torch.autograd.Function):
         dls = torch.empty(1, dtype=torch.float32, device=dev)
         lib = L.load()
         L.check(lib.ce_contrastive_bwd(L.ptr(img), L.ptr(txt), L.ptr(ls), L.ptr(labels_i), L.ptr(labels_t),
-                                       L.ptr(index_pos), B, BT, P, D, dt, L.ptr(gi), L.ptr(gt), L.ptr(dimg),
+                                       L.ptr(index_pos), B, BT, P, D, mode, dt, L.ptr(gi), L.ptr(gt), L.ptr(dimg),
                                        L.ptr(dtxt), L.ptr(dls), ws.data_ptr(), ws.numel(), L.stream_ptr()),
                 "contrastive backward")
-        return dimg, dtxt, dls.reshape(ctx.ls_shape).to(ctx.ls_dtype), None, None, None
+        return dimg, dtxt, dls.reshape(ctx.ls_shape).to(ctx.ls_dtype), None, None, None, None
 
 
 def contrastive_over_batch(image_features, text_features, logit_scale, labels_per_image,
                            labels_per_text, index_pos) -> Tuple[torch.Tensor, torch.Tensor]:
     """loss_i, loss_t of ``CriterionContrastive('ce')`` applied to ``CLIP.forward``'s over-batch logits."""
     return _ContrastiveOverBatch.apply(image_features, text_features, logit_scale, labels_per_image,
-                                       labels_per_text, index_pos)
+                                       labels_per_text, index_pos, "ce_overbatch")
+
+
+def contrastive_over_instance(image_features, text_features, logit_scale, labels_per_image,
+                              labels_per_text, index_pos, loss="ce") -> Tuple[torch.Tensor, torch.Tensor]:
+    """loss_i over each image's own T descriptions ('ce' or 'bce', model_clip.py:509-520,624-651) and
+    the over-batch text-side loss_t."""
+    if loss not in ("ce", "bce"):
+        raise RuntimeError("Invalid constrastive_loss '{}'. ".format(loss))
+    return _ContrastiveOverBatch.apply(image_features, text_features, logit_scale, labels_per_image,
+                                       labels_per_text, index_pos, loss + "_instance")
 
 
 def similarity_logits(a: torch.Tensor, b: torch.Tensor, logit_scale: torch.Tensor) -> torch.Tensor:

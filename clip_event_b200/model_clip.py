@@ -128,10 +128,21 @@ class CriterionContrastive(nn.Module):
             labels_per_text = torch.arange(B, device=dev)      # model_clip.py:638-640
         if index_pos is None:
             raise RuntimeError("index_pos is required (the reference index_selects with it, model_clip.py:655)")
-        if self.constrastive_loss != "ce" or not constrastive_overbatch:
-            raise RuntimeError("clip_event_b200: only constrastive_loss='ce' with constrastive_overbatch=True "
-                               "is implemented in this build")
-        loss_i, loss_t = F_.contrastive_over_batch(img, txt, ls, labels_per_image, labels_per_text, index_pos)
+        if self.constrastive_loss == "kl":
+            # the reference's 'kl' path is unusable: its collate_fn calls torch.zeros() with no shape
+            # (dataset_voa.py:642) and feeds raw logits to KLDivLoss (model_clip.py:628-629)
+            raise RuntimeError("constrastive_loss 'kl' is broken in the reference and not provided")
+        if logits_per_image.per_instance != (not constrastive_overbatch):
+            raise RuntimeError("constrastive_overbatch=%s does not match the logits the head produced "
+                               "(ClipEventHead.set_hyps)" % constrastive_overbatch)
+        if constrastive_overbatch:
+            if self.constrastive_loss != "ce":
+                # dataset_voa.py:628-631: "Set constrastive_overbatch=false for constrative_loss=='bce'."
+                raise RuntimeError("Set constrastive_overbatch=false for constrative_loss=='bce'.")
+            loss_i, loss_t = F_.contrastive_over_batch(img, txt, ls, labels_per_image, labels_per_text, index_pos)
+        else:
+            loss_i, loss_t = F_.contrastive_over_instance(img, txt, ls, labels_per_image, labels_per_text,
+                                                          index_pos, self.constrastive_loss)
         return {"loss_i": loss_i.to(img.dtype), "loss_t": loss_t.to(img.dtype)}
 
 

@@ -44,6 +44,11 @@ enum {
   CE_ERR_ARG = -6
 };
 enum { CE_F32 = 0, CE_BF16 = 1 };
+/* image-side loss of CriterionContrastive (model_clip.py:624-627, 646-651); the text side is always
+ * the over-batch cross-entropy of the positive descriptions (model_clip.py:504, 655-659) */
+enum { CE_IMG_CE_OVERBATCH = 0 /* labels_i: int64 [R] GLOBAL column of each image's positive      */,
+       CE_IMG_CE_INSTANCE = 1  /* labels_i: int64 [b] in [0,T), image vs its own T descriptions    */,
+       CE_IMG_BCE_INSTANCE = 2 /* labels_i: fp32 [b, T] targets, BCEWithLogits over the [b, T] tile */ };
 /* node-mask encodings accepted by the OT entry points */
 enum { CE_MASK_NUM_I64 = 0 /* reference `*_num`: int64, valid = nonzero  (model_clip.py:688-690) */,
        CE_MASK_PAD_U8 = 1  /* reference `*_pad`: bool/uint8, pad = nonzero (model_ot.py:66-74)   */ };
@@ -68,7 +73,9 @@ int ce_device_check(void);
  *   img          [R, D]   image_features (un-normalised)
  *   txt          [C, D]   text_features  (un-normalised), local columns
  *   logit_scale  [1]      fp32, the log of the temperature inverse (model_clip.py:330,502)
- *   labels_i     [R]      int64 GLOBAL column index of each image's positive  (labels_per_image)
+ *   labels_i     see image_loss; over batch: int64 [R] GLOBAL column index of each image's positive
+ *                (labels_per_image).  Over-instance modes score the b = C/T LOCAL images, which
+ *                are rows [row_offset, row_offset + b) of `img`, against their own T descriptions
  *   labels_t     [C]      int64 GLOBAL row index each local description belongs to (labels_per_text)
  *   index_pos    [P]      int64 LOCAL column indices used for the text-side loss  (index_pos)
  * ------------------------------------------------------------------------------------------ */
@@ -81,9 +88,10 @@ size_t ce_contrastive_workspace_bytes(int R, int C, int P, int D, int dtype);
  *   sums      [4]    fp32 out: {sum_p (colLSE_p - L[labels_t[pos_p], pos_p]), P, 0, 0}
  * Stashes norms / column LSE / split operands in `workspace` for the backward. */
 int ce_contrastive_fwd_partial(const void* img, const void* txt, const float* logit_scale,
-                               const int64_t* labels_i, const int64_t* labels_t,
+                               const void* labels_i, const int64_t* labels_t,
                                const int64_t* index_pos, int R, int C, int P, int D,
-                               int64_t col_offset, int dtype, float* row_part, float* sums,
+                               int64_t col_offset, int image_loss, int T, int64_t row_offset,
+                               int dtype, float* row_part, float* sums,
                                void* workspace, size_t workspace_bytes, ce_stream_t stream);
 
 /* Phase 2: merge `world` row_part blocks ([world, R, 4], this rank's own included), reduce the
@@ -102,9 +110,10 @@ int ce_contrastive_fwd_finish(const float* row_part_all, const float* sums_all, 
  *                                      ce_contrastive_bwd_finish on the local rows
  *   dlogit_scale_part [1] fp32      -- sum over ranks. */
 int ce_contrastive_bwd_partial(const void* img, const void* txt, const float* logit_scale,
-                               const int64_t* labels_i, const int64_t* labels_t,
+                               const void* labels_i, const int64_t* labels_t,
                                const int64_t* index_pos, int R, int C, int P, int D,
-                               int64_t col_offset, int dtype, const float* g_i, const float* g_t,
+                               int64_t col_offset, int image_loss, int T, int64_t row_offset,
+                               int dtype, const float* g_i, const float* g_t,
                                int R_total, int P_total, void* dtxt, float* dimg_hat_part,
                                float* dlogit_scale_part, void* workspace, size_t workspace_bytes,
                                ce_stream_t stream);
@@ -115,12 +124,12 @@ int ce_contrastive_bwd_finish(const void* img_rows, const float* dimg_hat_rows, 
 
 /* Single-GPU convenience wrappers (world = 1): forward then backward with the same workspace. */
 int ce_contrastive_fwd(const void* img, const void* txt, const float* logit_scale,
-                       const int64_t* labels_i, const int64_t* labels_t, const int64_t* index_pos,
-                       int B, int BT, int P, int D, int dtype, float* loss_i, float* loss_t,
+                       const void* labels_i, const int64_t* labels_t, const int64_t* index_pos,
+                       int B, int BT, int P, int D, int image_loss, int dtype, float* loss_i, float* loss_t,
                        void* workspace, size_t workspace_bytes, ce_stream_t stream);
 int ce_contrastive_bwd(const void* img, const void* txt, const float* logit_scale,
-                       const int64_t* labels_i, const int64_t* labels_t, const int64_t* index_pos,
-                       int B, int BT, int P, int D, int dtype, const float* g_i, const float* g_t,
+                       const void* labels_i, const int64_t* labels_t, const int64_t* index_pos,
+                       int B, int BT, int P, int D, int image_loss, int dtype, const float* g_i, const float* g_t,
                        void* dimg, void* dtxt, float* dlogit_scale, void* workspace,
                        size_t workspace_bytes, ce_stream_t stream);
 

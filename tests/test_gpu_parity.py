@@ -319,3 +319,70 @@ def test_error_behaviour_on_gpu():
         ce.CriterionAlignment()(torch.randn(2, 65, 16, device="cuda"), torch.randn(2, 9, 16, device="cuda"),
                                 torch.ones(2, 65, dtype=torch.int64, device="cuda"),
                                 torch.ones(2, 9, dtype=torch.int64, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------
+# over-instance image side: 'ce' and 'bce'  (model_clip.py:509-520, 624-651)
+# ------------------------------------------------------------------------------------------
+def run_instance(img, txt, ls, lpi, lpt, idx, loss):
+    head = ce.ClipEventHead(constrastive_overbatch=False).cuda()
+    with torch.no_grad():
+        head.logit_scale.copy_(ls)
+    ig, tg = img.cuda().requires_grad_(True), txt.cuda().requires_grad_(True)
+    a, b = head(ig, tg)
+    out = ce.CriterionContrastive(loss)(a, b, lpi.cuda(), lpt.cuda(), index_pos=idx.cuda(),
+                                        constrastive_overbatch=False)
+    (out["loss_i"].float() + out["loss_t"].float()).backward()
+    torch.cuda.synchronize()
+    return out["loss_i"].item(), out["loss_t"].item(), ig.grad.cpu(), tg.grad.cpu(), head.logit_scale.grad.item(), a
+
+
+@pytest.mark.parametrize("name,loss", [("contrastive_small_instance", "ce"), ("contrastive_small_bce", "bce")])
+def test_contrastive_instance_golden_full(name, loss):
+    g = load_golden(name)
+    li, lt, dimg, dtxt, dls, lazy = run_instance(_t(g["image_features"]), _t(g["text_features"]),
+                                                 torch.tensor(syn.LOGIT_SCALE_INIT), _t(g["labels_per_image"]),
+                                                 _t(g["labels_per_text"]), _t(g["index_pos"]), loss)
+    assert tuple(lazy.shape) == g["logits_per_image"].shape
+    assert rel_err(lazy.materialize().cpu(), g["logits_per_image"]) < 1e-5
+    assert close(li, g["loss_i"], F32_LOSS_RTOL, F32_LOSS_ATOL)
+    assert close(lt, g["loss_t"], F32_LOSS_RTOL, F32_LOSS_ATOL)
+    assert rel_err(dimg, g["dimg"]) < F32_GRAD
+    assert rel_err(dtxt, g["dtxt"]) < F32_GRAD
+    assert close(dls, g["dlogit_scale"], 1e-4, 1e-5)
+
+
+@pytest.mark.parametrize("loss", ["ce", "bce"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_contrastive_instance_vs_oracle_c2(loss, dtype):
+    B, T, D = 256, 9, 512
+    img, txt, ls = syn.contrastive_inputs(B, T, D, 17, "trained", dtype=dtype)
+    lpi, lpt, idx = syn.contrastive_labels(B, T, overbatch=False)
+    if loss == "bce":
+        lpi = torch.zeros(B, T)
+        lpi[:, 0] = 1.0
+    ref_losses, ref_grads = orc.loss_head_step(img.double(), txt.double(), ls.double(), lpi.double() if loss == "bce" else lpi,
+                                               lpt, idx, overbatch=False, kind=loss)
+    li, lt, dimg, dtxt, dls, _ = run_instance(img, txt, ls, lpi, lpt, idx, loss)
+    if dtype == torch.float32:
+        assert close(li, ref_losses["loss_i"].item(), F32_LOSS_RTOL, F32_LOSS_ATOL)
+        assert close(lt, ref_losses["loss_t"].item(), F32_LOSS_RTOL, F32_LOSS_ATOL)
+        assert rel_err(dimg, ref_grads["image_features"]) < F32_GRAD
+        assert rel_err(dtxt, ref_grads["text_features"]) < F32_GRAD
+        assert close(dls, ref_grads["logit_scale"].item(), 1e-4, 1e-5)
+    else:
+        assert close(li, ref_losses["loss_i"].item(), 4e-3, 1e-4) and close(lt, ref_losses["loss_t"].item(), 4e-3, 1e-4)
+        assert rel_err(dimg, ref_grads["image_features"]) < BF16_GRAD
+        assert rel_err(dtxt, ref_grads["text_features"]) < BF16_GRAD
+
+
+def test_criterion_mode_errors():
+    head = ce.ClipEventHead(constrastive_overbatch=True).cuda()
+    a, b = head(torch.randn(4, 16, device="cuda"), torch.randn(8, 16, device="cuda"))
+    idx = torch.arange(4, device="cuda") * 2
+    with pytest.raises(RuntimeError, match="constrastive_overbatch=false"):
+        ce.CriterionContrastive("bce")(a, b, index_pos=idx, constrastive_overbatch=True)
+    with pytest.raises(RuntimeError, match="kl"):
+        ce.CriterionContrastive("kl")(a, b, index_pos=idx)
+    with pytest.raises(RuntimeError, match="does not match"):
+        ce.CriterionContrastive("ce")(a, b, index_pos=idx, constrastive_overbatch=False)
