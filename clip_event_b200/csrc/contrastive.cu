@@ -374,20 +374,79 @@ __device__ __forceinline__ void warp_merge_ml(float& m, float& l) {
   m = M;
 }
 
-// Resolve the positives' columns for both GEMMs and clear their logit slots.
-__global__ void label_prep_kernel(const int64_t* labels_i, const int64_t* labels_t,
-                                  const int64_t* index_pos, int R, int C, int P, int64_t col_offset,
-                                  int* lab_local, float* lab_logit_i, int* lab_t, float* lab_logit_t) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < R) {
-    int64_t lab = labels_i != nullptr ? labels_i[i] - col_offset : -1;
-    lab_local[i] = (lab >= 0 && lab < C) ? (int)lab : -1;
-    lab_logit_i[i] = 0.f;
-  } else if (i < R + P) {
-    int p = i - R;
-    int64_t row = labels_t[index_pos[p]];
-    lab_t[p] = (row >= 0 && row < R) ? (int)row : -1;
-    lab_logit_t[p] = 0.f;
+// One launch for the whole forward preparation: norms (+ tf32 split / gathered copy) of the image
+// rows, the description rows and the positive descriptions, plus the label bookkeeping that used
+// to be three more launches.  One warp per row; rows are numbered img | txt | pos.
+struct PrepAllArgs {
+  const void* img; const void* txt;
+  const int64_t* labels_i; const int64_t* labels_t; const int64_t* index_pos;
+  int R, C, P, D;
+  int64_t col_offset;
+  float *rinv_i, *norm_i, *rinv_t, *norm_t, *rinv_p, *norm_p;
+  void *img0, *img1, *txt0, *txt1, *pos0, *pos1;
+  int *lab_local, *lab_t, *col_pos;          // col_pos is pre-set to -1 by a memset
+  float *lab_logit_i, *lab_logit_t;
+};
+template <int DT>
+__device__ __forceinline__ void prep_one_row(const void* src, int64_t sr, int r, int D, float* rinv,
+                                             float* norm, void* out0, void* out1) {
+  using T = typename In<DT>::type;
+  constexpr int V = In<DT>::kVec;
+  const int lane = threadIdx.x & 31;
+  const T* x = reinterpret_cast<const T*>(src) + sr * D;
+  float ss = 0.f;
+  for (int c = lane * V; c < D; c += 32 * V) {
+    float v[8];
+    In<DT>::load16(x + c, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) ss += v[i] * v[i];
+    if constexpr (DT == CE_F32) {
+      if (out0 != nullptr) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          hi[i] = __uint_as_float(f2tf32(v[i]));
+          lo[i] = __uint_as_float(f2tf32(v[i] - hi[i]));
+        }
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out0) + (int64_t)r * D + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out1) + (int64_t)r * D + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    } else {
+      if (out0 != nullptr)
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out0) + (int64_t)r * D + c) =
+            __ldg(reinterpret_cast<const uint4*>(x + c));
+    }
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) {
+    float n = sqrtf(ss);
+    if (rinv) rinv[r] = 1.f / n;
+    if (norm) norm[r] = n;
+  }
+}
+template <int DT>
+__global__ void prep_all_kernel(PrepAllArgs a) {
+  const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wi < a.R) {
+    prep_one_row<DT>(a.img, wi, wi, a.D, a.rinv_i, a.norm_i, a.img0, a.img1);
+    if (lane == 0) {
+      int64_t lab = a.labels_i != nullptr ? a.labels_i[wi] - a.col_offset : -1;
+      a.lab_local[wi] = (lab >= 0 && lab < a.C) ? (int)lab : -1;
+      a.lab_logit_i[wi] = 0.f;
+    }
+  } else if (wi < a.R + a.C) {
+    const int c = wi - a.R;
+    prep_one_row<DT>(a.txt, c, c, a.D, a.rinv_t, a.norm_t, a.txt0, a.txt1);
+  } else if (wi < a.R + a.C + a.P) {
+    const int p = wi - a.R - a.C;
+    const int64_t col = a.index_pos[p];
+    prep_one_row<DT>(a.txt, col, p, a.D, a.rinv_p, a.norm_p, a.pos0, a.pos1);
+    if (lane == 0) {
+      int64_t row = a.labels_t[col];
+      a.lab_t[p] = (row >= 0 && row < a.R) ? (int)row : -1;
+      a.lab_logit_t[p] = 0.f;
+      a.col_pos[col] = p;
+    }
   }
 }
 
@@ -585,24 +644,6 @@ __global__ void __launch_bounds__(1024) fwd_finish_kernel(const float4* row_part
   }
 }
 
-// col_pos[c] = p if description c is the p-th positive (index_pos[p] == c), else -1
-__global__ void col_pos_fill_kernel(int* col_pos, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) col_pos[c] = -1;
-}
-__global__ void col_pos_scatter_kernel(const int64_t* index_pos, int P, int* col_pos) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P) col_pos[index_pos[p]] = p;
-}
-
-// rows of dpos_hat *= |t_pos|  (one warp per row)
-__global__ void pos_scale_kernel(float* dpos, const int64_t* index_pos, const float* norm_t, int P, int D) {
-  int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (p >= P) return;
-  const float s = norm_t[index_pos[p]];
-  for (int c = lane; c < D; c += 32) dpos[(int64_t)p * D + c] *= s;
-}
-
 __global__ void __launch_bounds__(1024) sum_dls_kernel(const float* part, int n, float* out) {
   __shared__ double sh[32];
   double s = 0.0;
@@ -665,7 +706,7 @@ __global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, 
 // workspace
 // ------------------------------------------------------------------------------------------
 struct CtrWs {
-  float *rinv_i, *norm_i, *rinv_t, *norm_t, *rinv_p;
+  float *rinv_i, *norm_i, *rinv_t, *norm_t, *rinv_p, *norm_p;
   float *lse2_row, *lse2_col, *item_t;
   int *lab_local, *col_pos, *lab_t;
   float *lab_logit_i, *lab_logit_t;
@@ -694,7 +735,7 @@ CtrWs carve(void* base, int R, int C, int P, int D, int dtype) {
   w.tiles_gt = ((P + kBM - 1) / kBM) * w.nblk_t;
   w.rinv_i = cv.take<float>(R); w.norm_i = cv.take<float>(R);
   w.rinv_t = cv.take<float>(C); w.norm_t = cv.take<float>(C);
-  w.rinv_p = cv.take<float>(P);
+  w.rinv_p = cv.take<float>(P); w.norm_p = cv.take<float>(P);
   w.lse2_row = cv.take<float>(R); w.lse2_col = cv.take<float>(P); w.item_t = cv.take<float>(P);
   w.lab_local = cv.take<int>(R); w.col_pos = cv.take<int>(C); w.lab_t = cv.take<int>(P);
   w.lab_logit_i = cv.take<float>(R); w.lab_logit_t = cv.take<float>(P);
@@ -764,12 +805,22 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
   constexpr bool TF = DT == CE_F32;
   constexpr int BN = s_bn<DT>();
   const int64_t* labels_i = mode == 0 ? reinterpret_cast<const int64_t*>(labels_i_v) : nullptr;
-  CE_TRY(run_prep<DT>(img, nullptr, R, D, w.rinv_i, w.norm_i, TF ? w.img_p[0] : nullptr, w.img_p[1], st));
-  CE_TRY(run_prep<DT>(txt, nullptr, C, D, w.rinv_t, w.norm_t, TF ? w.txt_p[0] : nullptr, w.txt_p[1], st));
-  CE_TRY(run_prep<DT>(txt, index_pos, P, D, w.rinv_p, nullptr, w.pos_p[0], w.pos_p[1], st));
-  label_prep_kernel<<<(R + P + 255) / 256, 256, 0, st>>>(labels_i, labels_t, index_pos, R, C, P, col_offset,
-                                                         w.lab_local, w.lab_logit_i, w.lab_t, w.lab_logit_t);
-  CE_LAUNCH_CHECK();
+  CE_CUDA_TRY(cudaMemsetAsync(w.col_pos, 0xff, sizeof(int) * (size_t)C, st));   // -1 everywhere
+  {
+    PrepAllArgs pa{};
+    pa.img = img; pa.txt = txt; pa.labels_i = labels_i; pa.labels_t = labels_t; pa.index_pos = index_pos;
+    pa.R = R; pa.C = C; pa.P = P; pa.D = D; pa.col_offset = col_offset;
+    pa.rinv_i = w.rinv_i; pa.norm_i = w.norm_i; pa.rinv_t = w.rinv_t; pa.norm_t = w.norm_t;
+    pa.rinv_p = w.rinv_p; pa.norm_p = w.norm_p;
+    pa.img0 = TF ? w.img_p[0] : nullptr; pa.img1 = w.img_p[1];
+    pa.txt0 = TF ? w.txt_p[0] : nullptr; pa.txt1 = w.txt_p[1];
+    pa.pos0 = w.pos_p[0]; pa.pos1 = w.pos_p[1];
+    pa.lab_local = w.lab_local; pa.lab_t = w.lab_t; pa.col_pos = w.col_pos;
+    pa.lab_logit_i = w.lab_logit_i; pa.lab_logit_t = w.lab_logit_t;
+    const int64_t warps = (int64_t)R + C + P;
+    prep_all_kernel<DT><<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(pa);
+    CE_LAUNCH_CHECK();
+  }
   GemmOperand oi = operand<DT>(img, w.img_p, R, D, 0);
   GemmOperand ot = operand<DT>(txt, w.txt_p, C, D, 0);
   GemmOperand op = operand<DT>(w.pos_p[0], w.pos_p, P, D, 0);
@@ -837,10 +888,7 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
   (void)labels_t;
   constexpr bool TF = DT == CE_F32;
   constexpr int BN = s_bn<DT>();
-  col_pos_fill_kernel<<<(C + 255) / 256, 256, 0, st>>>(w.col_pos, C);
-  CE_LAUNCH_CHECK();
-  col_pos_scatter_kernel<<<(P + 255) / 256, 256, 0, st>>>(index_pos, P, w.col_pos);
-  CE_LAUNCH_CHECK();
+  (void)index_pos;   // col_pos (description -> positive slot) was built by the forward
   GemmOperand oi = operand<DT>(img, w.img_p, R, D, 0);
   GemmOperand ot = operand<DT>(txt, w.txt_p, C, D, 0);
   GemmOperand op = operand<DT>(w.pos_p[0], w.pos_p, P, D, 0);
@@ -883,11 +931,7 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
   // d T^ = s |t| G^t img  (+ s |t_pos| Gt img on the positive rows, added by the row kernel)
   if (mode == 0)
     CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, C, w.ldg, 1), iB, R, w.dtxt_hat, D, w.norm_t, ls, false, st)));
-  CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, P, w.ldgt, 0), iB, R, w.dpos_hat, D, nullptr, ls, false, st)));
-  // dpos_hat rows still miss the |t_pos| factor: norm_t[index_pos[p]]; fold it in the row kernel via
-  // the same normalisation (x^ . d and the final 1/|x| are linear in d) -- see normalize_bwd_kernel.
-  pos_scale_kernel<<<(P * 32 + 255) / 256, 256, 0, st>>>(w.dpos_hat, index_pos, w.norm_t, P, D);
-  CE_LAUNCH_CHECK();
+  CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, P, w.ldgt, 0), iB, R, w.dpos_hat, D, w.norm_p, ls, false, st)));
   normalize_bwd_kernel<DT><<<(C * 32 + 255) / 256, 256, 0, st>>>(txt, w.dtxt_hat, C, D, dtxt, w.col_pos, w.dpos_hat);
   CE_LAUNCH_CHECK();
   return CE_OK;
