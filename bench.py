@@ -226,7 +226,7 @@ def main():
             else:
                 loss_ot = crit_ot(leaves["etxt"], leaves["obj"], static["tnum"], static["onum"])["loss_ot"]
         if world > 1:
-            li, lt = cd.global_contrastive(leaves["img"], leaves["txt"], head.logit_scale, lpi, lpt, idx)
+            li, lt = cd.global_contrastive(leaves["img"], leaves["txt"], head.logit_scale, None, lpt, idx)  # canonical labels
             loss_dict = {"loss_i": li, "loss_t": lt}
         else:
             a, b_ = head(leaves["img"], leaves["txt"])
@@ -334,7 +334,7 @@ def main():
             t.grad = None
         head.logit_scale.grad = None
         if world > 1:
-            li, lt = cd.global_contrastive(leaves["img"], leaves["txt"], head.logit_scale, lpi, lpt, idx)
+            li, lt = cd.global_contrastive(leaves["img"], leaves["txt"], head.logit_scale, None, lpt, idx)  # canonical labels
         else:
             li, lt = F_.contrastive_over_batch(leaves["img"], leaves["txt"], head.logit_scale, lpi, lpt, idx)
         (li + lt).backward()

@@ -25,7 +25,7 @@ SIGNATURES = {
     "ce_device_check": (_i, []),
     "ce_contrastive_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "ce_contrastive_fwd_partial": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _i, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
-    "ce_contrastive_fwd_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ce_contrastive_fwd_finish": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "ce_contrastive_bwd_partial": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _i, _i64, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ce_contrastive_bwd_finish": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "ce_contrastive_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -613,15 +613,15 @@ __global__ void __launch_bounds__(1024) sum_items_kernel(const float* item_t, in
 }
 
 // Merge the per-rank row statistics, emit both losses and the global base-2 row LSE.
-__global__ void __launch_bounds__(1024) fwd_finish_kernel(const float4* row_part_all, const float* sums_all,
-                                                          int world, int R, float* lse2_row,
-                                                          float* loss_i, float* loss_t) {
+__global__ void __launch_bounds__(1024) fwd_finish_kernel(const float* row_part_all, const float* sums_all,
+                                                          int64_t rank_stride, int world, int R,
+                                                          float* lse2_row, float* loss_i, float* loss_t) {
   __shared__ double sh[32];
   double acc = 0.0;
   for (int r = threadIdx.x; r < R; r += 1024) {
     float m = -INFINITY, l = 0.f, lab = 0.f;
     for (int w = 0; w < world; ++w) {
-      float4 pr = row_part_all[(int64_t)w * R + r];
+      float4 pr = *reinterpret_cast<const float4*>(row_part_all + (int64_t)w * rank_stride + (int64_t)r * 4);
       float mn = fmaxf(m, pr.x);
       if (mn != -INFINITY) { l = l * ex2(m - mn) + pr.y * ex2(pr.x - mn); m = mn; }
       lab += pr.z;
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(1024) fwd_finish_kernel(const float4* row_part
     for (int i = 0; i < 32; ++i) t += sh[i];
     *loss_i = (float)(t / (double)R);
     double st = 0.0, sp = 0.0;
-    for (int w = 0; w < world; ++w) { st += (double)sums_all[w * 4]; sp += (double)sums_all[w * 4 + 1]; }
+    for (int w = 0; w < world; ++w) { st += (double)sums_all[w * rank_stride]; sp += (double)sums_all[w * rank_stride + 1]; }
     *loss_t = (float)(st / sp);
   }
 }
@@ -972,16 +972,18 @@ extern "C" int ce_contrastive_fwd_partial(const void* img, const void* txt, cons
   return fwd_partial_impl<CE_BF16>(img, txt, logit_scale, labels_i, labels_t, index_pos, R, C, P, D, col_offset, image_loss, T, row_offset, row_part, sums, w, st);
 }
 
-extern "C" int ce_contrastive_fwd_finish(const float* row_part_all, const float* sums_all, int world,
+extern "C" int ce_contrastive_fwd_finish(const float* row_part_all, const float* sums_all,
+                                         int64_t rank_stride, int world,
                                          int R, int C, int P, int D, int dtype, float* loss_i,
                                          float* loss_t, void* workspace, size_t workspace_bytes,
                                          ce_stream_t stream) {
   CE_TRY(check_device());
   if (world < 1) return fail(CE_ERR_ARG, "contrastive: world must be >= 1");
+  if (rank_stride % 4 != 0 || ((uintptr_t)row_part_all & 15)) return fail(CE_ERR_ALIGN, "contrastive: row statistics blocks must be 16-byte aligned");
   CtrWs w = carve(workspace, R, C, P, D, dtype);
   if (workspace_bytes < w.bytes) return fail(CE_ERR_WORKSPACE, "contrastive: workspace too small");
   fwd_finish_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float4*>(row_part_all), sums_all, world, R, w.lse2_row, loss_i, loss_t);
+      row_part_all, sums_all, rank_stride, world, R, w.lse2_row, loss_i, loss_t);
   CE_LAUNCH_CHECK();
   return CE_OK;
 }
@@ -1035,7 +1037,7 @@ extern "C" int ce_contrastive_fwd(const void* img, const void* txt, const float*
                                     image_loss, B > 0 ? BT / B : 1, 0, dtype,
                                     reinterpret_cast<float*>(w.row_part), w.sums, workspace,
                                     workspace_bytes, stream));
-  return ce_contrastive_fwd_finish(reinterpret_cast<const float*>(w.row_part), w.sums, 1, B, BT, P, D,
+  return ce_contrastive_fwd_finish(reinterpret_cast<const float*>(w.row_part), w.sums, 0, 1, B, BT, P, D,
                                    dtype, loss_i, loss_t, workspace, workspace_bytes, stream);
 }
 

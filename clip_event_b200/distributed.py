@@ -43,20 +43,21 @@ class CudaBackend:
         dt = L.dtype_code(img_all.dtype)
         nbytes = self.lib.ce_contrastive_workspace_bytes(R, C, P, D, dt)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=img_all.device)
-        row_part = torch.empty(R, 4, dtype=torch.float32, device=img_all.device)
-        sums = torch.empty(4, dtype=torch.float32, device=img_all.device)
+        stats = torch.empty(R * 4 + 4, dtype=torch.float32, device=img_all.device)   # [row_part | sums]
+        row_part, sums = stats[: R * 4], stats[R * 4:]
         L.check(self.lib.ce_contrastive_fwd_partial(
             img_all.data_ptr(), txt.data_ptr(), ls.data_ptr(), labels_i_all.data_ptr(), labels_t.data_ptr(),
             index_pos.data_ptr(), R, C, P, D, int(col_offset), L.CE_IMG_CE_OVERBATCH, 1, 0, dt,
             row_part.data_ptr(), sums.data_ptr(),
             ws.data_ptr(), nbytes, L.stream_ptr()), "contrastive fwd_partial")
-        return row_part, sums, (ws, R, C, P, D, dt)
+        return stats, (ws, R, C, P, D, dt)
 
-    def fwd_finish(self, row_part_all, sums_all, world, state):
+    def fwd_finish(self, stats_all, world, state):
+        """stats_all: [world, R*4 + 4] -- the all-gathered per-rank [row_part | sums] records."""
         ws, R, C, P, D, dt = state
         out = torch.empty(2, dtype=torch.float32, device=ws.device)
         L.check(self.lib.ce_contrastive_fwd_finish(
-            row_part_all.data_ptr(), sums_all.data_ptr(), world, R, C, P, D, dt, out.data_ptr(),
+            stats_all.data_ptr(), stats_all.data_ptr() + R * 16, R * 4 + 4, world, R, C, P, D, dt, out.data_ptr(),
             out.data_ptr() + 4, ws.data_ptr(), ws.numel(), L.stream_ptr()), "contrastive fwd_finish")
         return out[0], out[1]
 
@@ -117,7 +118,7 @@ class _GlobalContrastive(torch.autograd.Function):
         dev = img.device
         img_c, txt_c = img.detach().contiguous(), txt.detach().contiguous()
         ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-        labels_i = labels_i.to(device=dev, dtype=torch.int64).contiguous()
+        labels_i = None if labels_i is None else labels_i.to(device=dev, dtype=torch.int64).contiguous()
         labels_t = labels_t.to(device=dev, dtype=torch.int64).contiguous()
         index_pos = index_pos.to(device=dev, dtype=torch.int64).contiguous()
         b, D = img_c.shape
@@ -126,27 +127,27 @@ class _GlobalContrastive(torch.autograd.Function):
         img_all = torch.empty(world * b * D, dtype=img_c.dtype, device=dev)
         dist.all_gather_into_tensor(img_all, img_c.view(-1), group=group)
         img_all = img_all.view(world * b, D)
-        lab_all = torch.empty(world * b, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(lab_all, labels_i, group=group)
+        if labels_i is None:
+            # canonical contract (dataset_voa.py:617-621): image r's positive is column r*T -- no exchange
+            lab_all = torch.arange(world * b, dtype=torch.int64, device=dev) * (C // b)
+        else:
+            lab_all = torch.empty(world * b, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(lab_all, labels_i, group=group)
         # 2. local GEMM + statistics
         col_offset = rank * C
-        row_part, sums, state = compute.fwd_partial(img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset)
-        # 3. exchange the statistics
-        stats = torch.cat([row_part.reshape(-1), sums.reshape(-1)])
+        stats, state = compute.fwd_partial(img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset)
+        # 3. exchange the statistics: one record [row_part (R x 4) | sums (4)] per rank
         stats_all = torch.empty(world * stats.numel(), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(stats_all, stats, group=group)
         stats_all = stats_all.view(world, stats.numel())
-        R = world * b
-        row_part_all = stats_all[:, : R * 4].contiguous()
-        sums_all = stats_all[:, R * 4:].contiguous()
-        loss_i, loss_t = compute.fwd_finish(row_part_all, sums_all, world, state)
-        ctx.saved = (img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset, state, sums_all)
+        loss_i, loss_t = compute.fwd_finish(stats_all, world, state)
+        ctx.saved = (img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset, state)
         ctx.meta = (group, compute, world, rank, b, logit_scale.dtype, logit_scale.shape)
         return loss_i, loss_t
 
     @staticmethod
     def backward(ctx, g_i, g_t):
-        img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset, state, sums_all = ctx.saved
+        img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset, state = ctx.saved
         group, compute, world, rank, b, ls_dtype, ls_shape = ctx.meta
         dev = txt_c.device
         zero = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -170,8 +171,9 @@ def global_contrastive(image_features, text_features, logit_scale, labels_per_im
                        index_pos, group=None, compute=None):
     """loss_i, loss_t over the GLOBAL batch; gradients for this rank's images and descriptions.
 
-    ``labels_per_image`` are global column indices, ``labels_per_text`` global row indices and
-    ``index_pos`` local column indices (see :func:`global_labels_for_rank`).
+    ``labels_per_image`` are global column indices (None = the canonical ``row * T``, which needs
+    no exchange), ``labels_per_text`` global row indices and ``index_pos`` local column indices
+    (see :func:`global_labels_for_rank`).
     """
     if compute is None:
         compute = CudaBackend()

@@ -94,12 +94,14 @@ int ce_contrastive_fwd_partial(const void* img, const void* txt, const float* lo
                                int dtype, float* row_part, float* sums,
                                void* workspace, size_t workspace_bytes, ce_stream_t stream);
 
-/* Phase 2: merge `world` row_part blocks ([world, R, 4], this rank's own included), reduce the
- * `world` sums blocks ([world, 4]) and emit the losses.  loss_i = mean_r(rowLSE - L[r,label]),
+/* Phase 2: merge `world` row_part blocks (block w at row_part_all + w*rank_stride floats, [R, 4]
+ * each, this rank's own included), reduce the `world` sums blocks (block w at sums_all +
+ * w*rank_stride, [4] each) and emit the losses -- so one all-gathered buffer of per-rank
+ * [row_part | sums] records can be passed without repacking.  loss_i = mean_r(rowLSE - L[r,label]),
  * loss_t = mean_p(...) over the GLOBAL P.  Writes the global row LSE into the workspace (same
  * R, C, P, D, dtype as phase 1) for the backward. */
-int ce_contrastive_fwd_finish(const float* row_part_all, const float* sums_all, int world, int R,
-                              int C, int P, int D, int dtype, float* loss_i, float* loss_t,
+int ce_contrastive_fwd_finish(const float* row_part_all, const float* sums_all, int64_t rank_stride,
+                              int world, int R, int C, int P, int D, int dtype, float* loss_i, float* loss_t,
                               void* workspace, size_t workspace_bytes, ce_stream_t stream);
 
 /* Backward phase 1.  g_i / g_t are device scalars dL/dloss_i, dL/dloss_t; R_total / P_total the

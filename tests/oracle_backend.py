@@ -32,17 +32,19 @@ class OracleBackend:
         lab_rows = labels_t[index_pos]
         item_t = col_lse2 / LOG2E - Lp[lab_rows, torch.arange(index_pos.numel())] / LOG2E
         sums = torch.tensor([item_t.sum().item(), float(index_pos.numel()), 0.0, 0.0])
-        state = dict(L2=L2, ih=ih, th=th, col_lse2=col_lse2, lab=lab, local=local)
-        return row_part, sums, state
+        state = dict(L2=L2, ih=ih, th=th, col_lse2=col_lse2, lab=lab, local=local, R=R)
+        return torch.cat([row_part.reshape(-1), sums]), state
 
-    def fwd_finish(self, row_part_all, sums_all, world, state):
-        rp = row_part_all.view(world, -1, 4).double()
+    def fwd_finish(self, stats_all, world, state):
+        R = state["R"]
+        row_part_all, sums_all = stats_all[:, : R * 4], stats_all[:, R * 4:]
+        rp = row_part_all.reshape(world, -1, 4).double()
         m = rp[:, :, 0].max(0).values
         l = (rp[:, :, 1] * torch.exp2(rp[:, :, 0] - m)).sum(0)
         lse2 = m + torch.log2(l)
         state["lse2_row"] = lse2
         loss_i = (lse2 / LOG2E - rp[:, :, 2].sum(0)).mean()
-        sa = sums_all.view(world, 4).double()
+        sa = sums_all.reshape(world, 4).double()
         loss_t = sa[:, 0].sum() / sa[:, 1].sum()
         return loss_i.float(), loss_t.float()
 

@@ -36,7 +36,8 @@ def main():
             leaves = dict(img=img[lo:hi], txt=txt[lo * T:hi * T], etxt=etxt[lo:hi], obj=obj[lo:hi])
             leaves = {k: v.to(dev).requires_grad_(True) for k, v in leaves.items()}
             lsg = ls.to(dev).requires_grad_(True)
-            loss_i, loss_t = cd.global_contrastive(leaves["img"], leaves["txt"], lsg, li_, lt_, ip_)
+            loss_i, loss_t = cd.global_contrastive(leaves["img"], leaves["txt"], lsg,
+                                                   li_ if D == 512 else None, lt_, ip_)   # explicit and canonical labels
             loss_ot = cd.sharded_alignment(leaves["etxt"], leaves["obj"], tnum[lo:hi].to(dev), onum[lo:hi].to(dev))
             (loss_i + loss_t + loss_ot).backward()
             torch.cuda.synchronize()
