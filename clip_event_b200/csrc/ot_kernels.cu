@@ -79,6 +79,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// A fragment (m16 x k16, bf16) of diag(v0 at rows 0-7, v1 at rows 8-15): thread (g, t) holds the
+// diagonal element of row g in a0 and of row g+8 in a3 when 2t or 2t+1 equals g.
+__device__ __forceinline__ void diag_frag(uint32_t* af, float v_g, float v_g8, int g, int t) {
+  const float z = 0.f;
+  af[0] = pack_bf16(2 * t == g ? v_g : z, 2 * t + 1 == g ? v_g : z);
+  af[1] = 0u;
+  af[2] = 0u;
+  af[3] = pack_bf16(2 * t == g ? v_g8 : z, 2 * t + 1 == g ? v_g8 : z);
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
 // ---- cp.async ring: every stage holds one 128-byte column slab of [x rows | y rows] ----------
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src),
@@ -143,6 +154,16 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
   float acc[TPW][NJ][4];
   float yss[TPW][2];
   float xss[NJ];
+  float yd[F32 ? 1 : TPW][2][4];        // bf16: diagonal blocks of tile * tile^t (sums of squares)
+  float xd[F32 ? 1 : MP / 16][2][4];
+#pragma unroll
+  for (int i = 0; i < (F32 ? 1 : TPW); ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) yd[i][0][c] = yd[i][1][c] = 0.f;
+#pragma unroll
+  for (int q = 0; q < (F32 ? 1 : MP / 16); ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xd[q][0][c] = xd[q][1][c] = 0.f;
 #pragma unroll
   for (int i = 0; i < TPW; ++i) {
     yss[i][0] = yss[i][1] = 0.f;
@@ -212,7 +233,10 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
         }
       }
     } else {
-      // bf16 mode: products of bf16 inputs are exact in the fp32 accumulator
+      // bf16 mode: products of bf16 inputs are exact in the fp32 accumulator.  The row sums of
+      // squares also come from the tensor core: the diagonal of tile * tile^t, whose B fragments
+      // are the tile's own A-fragment registers ({a0,a2} = rows 0-7, {a1,a3} = rows 8-15) -- this
+      // replaces 16 unpack+FMA instructions per fragment on the (saturated) FMA/ALU pipes.
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {          // 4 x k16 per 64-column slab
         uint32_t bf[NJ][2];
@@ -220,8 +244,15 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
         for (int j = 0; j < NJ; ++j) {
           bf[j][0] = xs[(8 * j + g) * RSW + ks * 8 + t];
           bf[j][1] = xs[(8 * j + g) * RSW + ks * 8 + t + 4];
-          float p0 = bf_lo(bf[j][0]), p1 = bf_hi(bf[j][0]), p2 = bf_lo(bf[j][1]), p3 = bf_hi(bf[j][1]);
-          xss[j] += p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3;
+        }
+        if (w == 0) {
+#pragma unroll
+          for (int q = 0; q < MP / 16; ++q) {
+            const uint32_t xa[4] = {bf[2 * q][0], bf[2 * q + 1][0], bf[2 * q][1], bf[2 * q + 1][1]};
+            const uint32_t b_lo[2] = {xa[0], xa[2]}, b_hi[2] = {xa[1], xa[3]};
+            mma_bf16(xd[q][0], xa, b_lo);
+            mma_bf16(xd[q][1], xa, b_hi);
+          }
         }
 #pragma unroll
         for (int i = 0; i < TPW; ++i) {
@@ -229,10 +260,9 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
           if (tile < my_tiles) {
             const uint32_t* yr = ys + (tile * 16 + g) * RSW + ks * 8 + t;
             uint32_t af[4] = {yr[0], yr[8 * RSW], yr[4], yr[8 * RSW + 4]};
-            yss[i][0] += bf_lo(af[0]) * bf_lo(af[0]) + bf_hi(af[0]) * bf_hi(af[0]) +
-                         bf_lo(af[2]) * bf_lo(af[2]) + bf_hi(af[2]) * bf_hi(af[2]);
-            yss[i][1] += bf_lo(af[1]) * bf_lo(af[1]) + bf_hi(af[1]) * bf_hi(af[1]) +
-                         bf_lo(af[3]) * bf_lo(af[3]) + bf_hi(af[3]) * bf_hi(af[3]);
+            const uint32_t b_lo[2] = {af[0], af[2]}, b_hi[2] = {af[1], af[3]};
+            mma_bf16(yd[i][0], af, b_lo);
+            mma_bf16(yd[i][1], af, b_hi);
 #pragma unroll
             for (int j = 0; j < NJ; ++j) mma_bf16(acc[i][j], af, bf[j]);
           }
@@ -248,12 +278,19 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
     int tile = w + i * NWARPS;
     if (tile < my_tiles) {
       int r = tile * 16 + g;
-      float s0 = yss[i][0], s1 = yss[i][1];
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      if (t == 0) {
+      if constexpr (F32) {
+        float s0 = yss[i][0], s1 = yss[i][1];
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        if (t == 0) {
+          if (r < rows_valid) a.ny2[(int64_t)b * a.Nld + row0 + r] = s0;
+          if (r + 8 < rows_valid) a.ny2[(int64_t)b * a.Nld + row0 + r + 8] = s1;
+        }
+      } else if (t == (g >> 1)) {   // this thread holds the diagonal elements (g, g) and (g+8, g+8)
+        const float s0 = (g & 1) ? yd[i][0][1] : yd[i][0][0];
+        const float s1 = (g & 1) ? yd[i][1][3] : yd[i][1][2];
         if (r < rows_valid) a.ny2[(int64_t)b * a.Nld + row0 + r] = s0;
         if (r + 8 < rows_valid) a.ny2[(int64_t)b * a.Nld + row0 + r + 8] = s1;
       }
@@ -269,12 +306,20 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_cost_kernel(OtArgs a) {
     }
   }
   if (ns == 0 && w == 0) {
+    if constexpr (F32) {
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      float v = xss[j];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (t == 0) a.nx2[(int64_t)b * MP + 8 * j + g] = v;
+      for (int j = 0; j < NJ; ++j) {
+        float v = xss[j];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (t == 0) a.nx2[(int64_t)b * MP + 8 * j + g] = v;
+      }
+    } else if (t == (g >> 1)) {
+#pragma unroll
+      for (int q = 0; q < MP / 16; ++q) {
+        a.nx2[(int64_t)b * MP + 16 * q + g] = (g & 1) ? xd[q][0][1] : xd[q][0][0];
+        a.nx2[(int64_t)b * MP + 16 * q + g + 8] = (g & 1) ? xd[q][1][3] : xd[q][1][2];
+      }
     }
   }
 }
@@ -822,7 +867,7 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
       if constexpr (F32) {
         *reinterpret_cast<float4*>(Ws + r * LDW + c) = v;
       } else {
-        uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        uint2 pk = make_uint2(pack_bf16(-v.x, -v.y), pack_bf16(-v.z, -v.w));   // -W: no sign flip later
         *reinterpret_cast<uint2*>(Wb + r * LDWB + c) = pk;
       }
     }
@@ -872,6 +917,8 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
             }
           }
         } else {
+          // acc = (-W^t) x + diag(ay) y : the elementwise term rides on the tensor core as two more
+          // k-steps (ay split into bf16 hi + lo), so the epilogue below is only pack + store
 #pragma unroll
           for (int ks = 0; ks < MP / 16; ++ks) {
             const uint32_t* wr = reinterpret_cast<const uint32_t*>(Wb + (tile * 16 + g) * LDWB + ks * 16) + t;
@@ -883,20 +930,37 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
               mma_bf16(acc[j], af, bf);
             }
           }
+          const float ay0 = ays[tile * 16 + g], ay1 = ays[tile * 16 + g + 8];
+          const float ay0h = bf16_round(ay0), ay1h = bf16_round(ay1);
+          uint32_t dh[4], dl[4];
+          diag_frag(dh, ay0h, ay1h, g, t);
+          diag_frag(dl, ay0 - ay0h, ay1 - ay1h, g, t);
+          const uint8_t* ytile = stage + (MP + tile * 16 + (lane & 15)) * RS;
+#pragma unroll
+          for (int j = 0; j < DC / 8; ++j) {
+            uint32_t bf[2];
+            ldsm_x2_trans(bf, ytile + j * 16);
+            mma_bf16(acc[j], dh, bf);
+            mma_bf16(acc[j], dl, bf);
+          }
         }
         int r = tile * 16 + g;
+        if constexpr (!F32) {
+#pragma unroll
+          for (int j = 0; j < DC / 8; ++j) {
+            int d = 8 * j + 2 * t;
+            if (d0 + d < a.D) {
+              if (r < rows_valid) store2<DT>(dyg + (int64_t)r * a.D + d0 + d, acc[j][0], acc[j][1]);
+              if (r + 8 < rows_valid) store2<DT>(dyg + (int64_t)(r + 8) * a.D + d0 + d, acc[j][2], acc[j][3]);
+            }
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < DC / 8; ++j) {
           int d = 8 * j + 2 * t;
           if (d0 + d < a.D) {
-            float y00, y01, y10, y11;
-            if constexpr (F32) {
-              y00 = __uint_as_float(ys[r * RSW + d]); y01 = __uint_as_float(ys[r * RSW + d + 1]);
-              y10 = __uint_as_float(ys[(r + 8) * RSW + d]); y11 = __uint_as_float(ys[(r + 8) * RSW + d + 1]);
-            } else {
-              uint32_t u0 = ys[r * RSW + d / 2], u1 = ys[(r + 8) * RSW + d / 2];
-              y00 = bf_lo(u0); y01 = bf_hi(u0); y10 = bf_lo(u1); y11 = bf_hi(u1);
-            }
+            float y00 = __uint_as_float(ys[r * RSW + d]), y01 = __uint_as_float(ys[r * RSW + d + 1]);
+            float y10 = __uint_as_float(ys[(r + 8) * RSW + d]), y11 = __uint_as_float(ys[(r + 8) * RSW + d + 1]);
             if (r < rows_valid) {
               float ay = ays[r];
               store2<DT>(dyg + (int64_t)r * a.D + d0 + d, ay * y00 - acc[j][0], ay * y01 - acc[j][1]);
@@ -906,6 +970,7 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
               store2<DT>(dyg + (int64_t)(r + 8) * a.D + d0 + d, ay * y10 - acc[j][2], ay * y11 - acc[j][3]);
             }
           }
+        }
         }
       }
     }
@@ -953,19 +1018,22 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
             uint32_t u0 = xs[m * RSW + d / 2], u1 = xs[(m + 8) * RSW + d / 2];
             x00 = bf_lo(u0); x01 = bf_hi(u0); x10 = bf_lo(u1); x11 = bf_hi(u1);
           }
+          constexpr float sgn = F32 ? -1.f : 1.f;   // the bf16 copy of W already carries the minus sign
           if (a.nsplit == 1) {
-            if (m < a.M) store2<DT>(dxg + (int64_t)m * a.D + d0 + d, axs[m] * x00 - acc[0], axs[m] * x01 - acc[1]);
+            if (m < a.M)
+              store2<DT>(dxg + (int64_t)m * a.D + d0 + d, fmaf(axs[m], x00, sgn * acc[0]), fmaf(axs[m], x01, sgn * acc[1]));
             if (m + 8 < a.M)
-              store2<DT>(dxg + (int64_t)(m + 8) * a.D + d0 + d, axs[m + 8] * x10 - acc[2], axs[m + 8] * x11 - acc[3]);
+              store2<DT>(dxg + (int64_t)(m + 8) * a.D + d0 + d, fmaf(axs[m + 8], x10, sgn * acc[2]),
+                         fmaf(axs[m + 8], x11, sgn * acc[3]));
           } else {
             float* dacc = a.dx_acc + ((int64_t)b * a.M) * a.D + d0 + d;
             if (m < a.M) {
-              atomicAdd(dacc + (int64_t)m * a.D, -acc[0]);
-              atomicAdd(dacc + (int64_t)m * a.D + 1, -acc[1]);
+              atomicAdd(dacc + (int64_t)m * a.D, sgn * acc[0]);
+              atomicAdd(dacc + (int64_t)m * a.D + 1, sgn * acc[1]);
             }
             if (m + 8 < a.M) {
-              atomicAdd(dacc + (int64_t)(m + 8) * a.D, -acc[2]);
-              atomicAdd(dacc + (int64_t)(m + 8) * a.D + 1, -acc[3]);
+              atomicAdd(dacc + (int64_t)(m + 8) * a.D, sgn * acc[2]);
+              atomicAdd(dacc + (int64_t)(m + 8) * a.D + 1, sgn * acc[3]);
             }
           }
         }
@@ -1192,7 +1260,7 @@ int launch_ipot_mp(const IpotArgs& a, int N, cudaStream_t st, bool* handled) {
   static const int variant = getenv("CE_IPOT_VARIANT") ? atoi(getenv("CE_IPOT_VARIANT")) : 0;  // tuning aid
 #define CE_IPOT_CASE(COND, R, G, ...) \
   if (COND <= R) { ot_ipot_kernel<MP, R, G, ##__VA_ARGS__><<<(G == 32 ? (a.B + 7) / 8 : a.B), (G < 256 ? 256 : G), 0, st>>>(a); return CE_OK; }
-  CE_IPOT_CASE(rptw, 2, 32) CE_IPOT_CASE(rptw, 4, 32) CE_IPOT_CASE(rptw, 7, 32) CE_IPOT_CASE(rptw, 10, 32)
+  CE_IPOT_CASE(rptw, 2, 32, 2) CE_IPOT_CASE(rptw, 4, 32, 2) CE_IPOT_CASE(rptw, 7, 32, 2) CE_IPOT_CASE(rptw, 10, 32)
   CE_IPOT_CASE(rpt256, 1, 256) CE_IPOT_CASE(rpt256, 2, 256) CE_IPOT_CASE(rpt256, 4, 256)
   if (MP == 32 && variant == 1) { CE_IPOT_CASE(rpt256, 9, 256, 1, 0) }
   if (MP == 32 && variant == 2) { CE_IPOT_CASE(rpt512, 5, 512, 1, 0) }
