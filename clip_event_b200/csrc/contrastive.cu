@@ -674,30 +674,75 @@ __global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, 
   const float* dr = d + (int64_t)r * D;
   const int ei = extra_idx != nullptr ? extra_idx[r] : -1;
   const float* er = ei >= 0 ? extra + (int64_t)ei * D : nullptr;
+  // one pass: the row (x and d) stays in registers for D <= 32 * V * kMaxIter
+  constexpr int kMaxIter = 4;
+  float xv[kMaxIter][8], dv[kMaxIter][8];
   float n2 = 0.f, dot = 0.f;
-  for (int c = lane * V; c < D; c += 32 * V) {
-    float v[8];
-    In<DT>::load16(x + c, v);
+  const bool fits = D <= 32 * V * kMaxIter;
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float dv = dr[c + i] + (er != nullptr ? er[c + i] : 0.f);
-      n2 += v[i] * v[i];
-      dot += v[i] * dv;
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int c = (it * 32 + lane) * V;
+    if (c < D) {
+      In<DT>::load16(x + c, xv[it]);
+#pragma unroll
+      for (int q = 0; q < V; q += 4) {
+        float4 t4 = __ldg(reinterpret_cast<const float4*>(dr + c + q));
+        if (er != nullptr) {
+          const float4 e4 = __ldg(reinterpret_cast<const float4*>(er + c + q));
+          t4.x += e4.x; t4.y += e4.y; t4.z += e4.z; t4.w += e4.w;
+        }
+        dv[it][q] = t4.x; dv[it][q + 1] = t4.y; dv[it][q + 2] = t4.z; dv[it][q + 3] = t4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) { n2 = fmaf(xv[it][i], xv[it][i], n2); dot = fmaf(xv[it][i], dv[it][i], dot); }
+    }
+  }
+  if (!fits) {   // long rows: finish the reductions with a streaming loop
+    for (int c = (kMaxIter * 32 + lane) * V; c < D; c += 32 * V) {
+      float v[8];
+      In<DT>::load16(x + c, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float dd = dr[c + i] + (er != nullptr ? er[c + i] : 0.f);
+        n2 = fmaf(v[i], v[i], n2);
+        dot = fmaf(v[i], dd, dot);
+      }
     }
   }
   n2 = warp_sum(n2);
   dot = warp_sum(dot);
   float rinv = rsqrtf(n2);
   rinv = rinv * (1.5f - 0.5f * n2 * rinv * rinv);  // one Newton step: full fp32 accuracy
-  float coef = dot * rinv * rinv;
+  const float coef = dot * rinv * rinv;
   T* o = reinterpret_cast<T*>(out) + (int64_t)r * D;
-  for (int c = lane * V; c < D; c += 32 * V) {
-    float v[8];
-    In<DT>::load16(x + c, v);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float dv = dr[c + i] + (er != nullptr ? er[c + i] : 0.f);
-      In<DT>::st(o + c + i, (dv - v[i] * coef) * rinv);
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int c = (it * 32 + lane) * V;
+    if (c < D) {
+      float res[8];
+#pragma unroll
+      for (int i = 0; i < V; ++i) res[i] = (dv[it][i] - xv[it][i] * coef) * rinv;
+      if constexpr (DT == CE_F32) {
+        *reinterpret_cast<float4*>(o + c) = make_float4(res[0], res[1], res[2], res[3]);
+      } else {
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(res[0], res[1]), t1 = __floats2bfloat162_rn(res[2], res[3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(res[4], res[5]), t3 = __floats2bfloat162_rn(res[6], res[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(o + c) = pk;
+      }
+    }
+  }
+  if (!fits) {
+    for (int c = (kMaxIter * 32 + lane) * V; c < D; c += 32 * V) {
+      float v[8];
+      In<DT>::load16(x + c, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float dd = dr[c + i] + (er != nullptr ? er[c + i] : 0.f);
+        In<DT>::st(o + c + i, (dd - v[i] * coef) * rinv);
+      }
     }
   }
 }

@@ -104,19 +104,32 @@ constexpr int kSlabBytes = 128;   // bytes of one row staged per step (32 fp32 /
 constexpr int kStages = 2;
 
 // Stage slab `c` of the MP text rows followed by `rows` image rows; RS = smem row stride in bytes.
+// A thread always copies the same 16-byte column piece (nthreads is a multiple of 8), so the loop
+// only walks rows: no divisions, one bounds test per row.
 template <int RS>
 __device__ __forceinline__ void issue_slab(uint8_t* stage, const uint8_t* xg, const uint8_t* yg,
                                            int MP, int M, int rows, int rows_valid, int row_bytes,
                                            int c, int nthreads) {
-  const int total = (MP + rows) * (kSlabBytes / 16);
-  const int col0 = c * kSlabBytes;
-  for (int idx = threadIdx.x; idx < total; idx += nthreads) {
-    const int r = idx >> 3, piece = (idx & 7) * 16;
-    const bool is_x = r < MP;
-    const int rr = is_x ? r : r - MP;
-    const bool valid = (is_x ? rr < M : rr < rows_valid) && (col0 + piece < row_bytes);
-    const uint8_t* src = (is_x ? xg : yg) + (valid ? (int64_t)rr * row_bytes + col0 + piece : 0);
-    cp_async16(stage + r * RS + piece, src, valid);
+  const int piece = (threadIdx.x & 7) * 16;
+  const int col = c * kSlabBytes + piece;
+  const bool col_ok = col < row_bytes;
+  const int rstep = nthreads >> 3;
+  const int r0 = threadIdx.x >> 3;
+  {
+    const uint8_t* src = xg + (int64_t)r0 * row_bytes + col;
+    uint8_t* dst = stage + r0 * RS + piece;
+    for (int r = r0; r < MP; r += rstep, src += (int64_t)rstep * row_bytes, dst += rstep * RS) {
+      const bool valid = col_ok && r < M;
+      cp_async16(dst, valid ? src : xg, valid);
+    }
+  }
+  {
+    const uint8_t* src = yg + (int64_t)r0 * row_bytes + col;
+    uint8_t* dst = stage + (MP + r0) * RS + piece;
+    for (int r = r0; r < rows; r += rstep, src += (int64_t)rstep * row_bytes, dst += rstep * RS) {
+      const bool valid = col_ok && r < rows_valid;
+      cp_async16(dst, valid ? src : yg, valid);
+    }
   }
 }
 
@@ -946,12 +959,21 @@ __global__ void __launch_bounds__(NWARPS * 32) ot_grad_kernel(OtArgs a) {
         }
         int r = tile * 16 + g;
         if constexpr (!F32) {
+          T* p0 = dyg + (int64_t)r * a.D + d0 + 2 * t;
+          T* p1 = p0 + (int64_t)8 * a.D;
+          if (tile * 16 + 16 <= rows_valid && d0 + DC <= a.D) {     // interior tile: no per-store tests
 #pragma unroll
-          for (int j = 0; j < DC / 8; ++j) {
-            int d = 8 * j + 2 * t;
-            if (d0 + d < a.D) {
-              if (r < rows_valid) store2<DT>(dyg + (int64_t)r * a.D + d0 + d, acc[j][0], acc[j][1]);
-              if (r + 8 < rows_valid) store2<DT>(dyg + (int64_t)(r + 8) * a.D + d0 + d, acc[j][2], acc[j][3]);
+            for (int j = 0; j < DC / 8; ++j) {
+              store2<DT>(p0 + 8 * j, acc[j][0], acc[j][1]);
+              store2<DT>(p1 + 8 * j, acc[j][2], acc[j][3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < DC / 8; ++j) {
+              if (d0 + 8 * j + 2 * t < a.D) {
+                if (r < rows_valid) store2<DT>(p0 + 8 * j, acc[j][0], acc[j][1]);
+                if (r + 8 < rows_valid) store2<DT>(p1 + 8 * j, acc[j][2], acc[j][3]);
+              }
             }
           }
         } else {
