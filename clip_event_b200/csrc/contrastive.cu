@@ -46,21 +46,28 @@ struct EpiStats {
   float kk, rinv_r, m2, l;
   int lab;
   bool fixed_ref;
-  __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et2) {
-    for (int c = et2; c < BN; c += kEpiThreads) {
-      int col = n_blk * BN + c;
-      s_epi[c] = col < p.N ? __ldg(p.rinv_col + col) : 0.f;
-    }
-  }
-  __device__ __forceinline__ void row_begin(int row, bool ok) {
+  float pf_col, pf_rinv;
+  int pf_lab;
+  __device__ __forceinline__ void init() {
     kk = expf(__ldg(p.logit_scale)) * kLog2e;          // base-2 temperature
-    rinv_r = ok ? __ldg(p.rinv_row + row) : 0.f;
     // |cos| <= 1 bounds every scaled logit by kk: with a fixed reference the online max and its
     // rescaling disappear.  2^(-2 kk) must stay a normal float, so only for kk <= 40 (s <= 27.7).
     fixed_ref = kk <= 40.f;
+  }
+  __device__ __forceinline__ void prefetch(int n_blk, int et2, int row, bool ok) {
+    const int col = n_blk * BN + et2;
+    pf_col = (et2 < BN && col < p.N) ? __ldg(p.rinv_col + col) : 0.f;
+    pf_rinv = ok ? __ldg(p.rinv_row + row) : 0.f;
+    pf_lab = ok ? __ldg(p.lab + row) : -1;
+  }
+  __device__ __forceinline__ void tile_begin(float* s_epi, int et2) {
+    if (et2 < BN) s_epi[et2] = pf_col;
+  }
+  __device__ __forceinline__ void row_begin(int, bool) {
+    rinv_r = pf_rinv;
     m2 = fixed_ref ? kk : -INFINITY;
     l = 0.f;
-    lab = ok ? __ldg(p.lab + row) : -1;
+    lab = pf_lab;
   }
   __device__ __forceinline__ void chunk(const float* acc, int col0, int lcol0, const float* s_epi,
                                         int row, bool) {
@@ -132,20 +139,31 @@ struct EpiGrad {
   static constexpr int kRowBytes = (BN / 2) * 2 + 16;
   static constexpr int kStageBytesPerWarp = TF32X3 ? 0 : 32 * kRowBytes;
   uint8_t* stage;
-  float sl, kr, lse2r, cs, dls;
+  float sl, kr, lse2r, cs, dls, cs_all;
   int lab;
-  __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et2) {
-    for (int c = et2; c < BN; c += kEpiThreads) {
-      int col = n_blk * BN + c;
-      s_epi[c] = col < p.N ? __ldg(p.rinv_col + col) : 0.f;
-    }
-  }
-  __device__ __forceinline__ void row_begin(int row, bool ok) {
+  float pf_col, pf_rinv, pf_lse;
+  int pf_lab;
+  bool pf_ok;
+  __device__ __forceinline__ void init() {
     sl = expf(__ldg(p.logit_scale)) * kLog2e;
-    kr = ok ? sl * __ldg(p.rinv_row + row) : 0.f;
-    lse2r = ok ? __ldg(p.lse2_row + row) : 0.f;        // rows past M: v = 0, g = cs * 1 = 0
-    lab = ok ? __ldg(p.lab_row + row) : -1;
-    cs = ok ? __ldg(p.g) * p.inv_count / sl : 0.f;
+    cs_all = __ldg(p.g) * p.inv_count / sl;
+  }
+  __device__ __forceinline__ void prefetch(int n_blk, int et2, int row, bool ok) {
+    const int col = n_blk * BN + et2;
+    pf_col = (et2 < BN && col < p.N) ? __ldg(p.rinv_col + col) : 0.f;
+    pf_rinv = ok ? __ldg(p.rinv_row + row) : 0.f;
+    pf_lse = ok ? __ldg(p.lse2_row + row) : 0.f;        // rows past M: v = 0, g = cs * 1 = 0
+    pf_lab = ok ? __ldg(p.lab_row + row) : -1;
+    pf_ok = ok;
+  }
+  __device__ __forceinline__ void tile_begin(float* s_epi, int et2) {
+    if (et2 < BN) s_epi[et2] = pf_col;
+  }
+  __device__ __forceinline__ void row_begin(int, bool) {
+    kr = sl * pf_rinv;
+    lse2r = pf_lse;
+    lab = pf_lab;
+    cs = pf_ok ? cs_all : 0.f;
     dls = 0.f;
   }
   __device__ __forceinline__ void chunk(const float* acc, int col0, int lcol0, const float* s_epi,
@@ -153,20 +171,27 @@ struct EpiGrad {
     float gs[32];
     const float4* rc4 = reinterpret_cast<const float4*>(s_epi + lcol0);
     if (col0 + 32 <= p.N) {
+      // packed f32x2 arithmetic: the FMA pipe issues one warp instruction every two cycles, and
+      // this loop is what keeps the epilogue slower than the tensor core
+      const float2 kr2 = make_float2(kr, kr), nl2 = make_float2(-lse2r, -lse2r), cs2 = make_float2(cs, cs);
+      float2 dls2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i4 = 0; i4 < 8; ++i4) {
         const float4 r4 = rc4[i4];
-        const float rcv[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = 4 * i4 + j;
-          const float t = kr * rcv[j];
-          const float v = fmaf(acc[i], t, -lse2r);
-          const float g = cs * ex2(v);
-          dls = fmaf(g, v, dls);
-          gs[i] = g * t;
+        for (int h = 0; h < 2; ++h) {
+          const int i = 4 * i4 + 2 * h;
+          const float2 rc2 = h == 0 ? make_float2(r4.x, r4.y) : make_float2(r4.z, r4.w);
+          const float2 t2 = __fmul2_rn(kr2, rc2);
+          const float2 v2 = __ffma2_rn(make_float2(acc[i], acc[i + 1]), t2, nl2);
+          const float2 g2 = __fmul2_rn(cs2, make_float2(ex2(v2.x), ex2(v2.y)));
+          dls2 = __ffma2_rn(g2, v2, dls2);
+          const float2 o2 = __fmul2_rn(g2, t2);
+          gs[i] = o2.x;
+          gs[i + 1] = o2.y;
         }
       }
+      dls += dls2.x + dls2.y;
     } else {   // last, ragged column tile: columns past N must not contribute
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -264,17 +289,19 @@ struct EpiStore {
   static constexpr int kStageBytesPerWarp = 0;
   uint8_t* stage;
   Params p;
-  float rs;
-  __device__ __forceinline__ void tile_begin(float* s_epi, int, int n_blk, int et2) {
-    for (int c = et2; c < BN; c += kEpiThreads) {
-      int col = n_blk * BN + c;
-      s_epi[c] = (p.colscale != nullptr && col < p.N) ? __ldg(p.colscale + col) : 1.f;
-    }
+  float rs, alpha, pf_col, pf_rs;
+  __device__ __forceinline__ void init() {
+    alpha = p.logit_scale != nullptr ? expf(__ldg(p.logit_scale)) : 1.f;
   }
-  __device__ __forceinline__ void row_begin(int row, bool ok) {
-    rs = p.logit_scale != nullptr ? expf(__ldg(p.logit_scale)) : 1.f;
-    if (p.rowscale != nullptr && ok) rs *= __ldg(p.rowscale + row);
+  __device__ __forceinline__ void prefetch(int n_blk, int et2, int row, bool ok) {
+    const int col = n_blk * BN + et2;
+    pf_col = (p.colscale != nullptr && et2 < BN && col < p.N) ? __ldg(p.colscale + col) : 1.f;
+    pf_rs = (p.rowscale != nullptr && ok) ? __ldg(p.rowscale + row) : 1.f;
   }
+  __device__ __forceinline__ void tile_begin(float* s_epi, int et2) {
+    if (et2 < BN) s_epi[et2] = pf_col;
+  }
+  __device__ __forceinline__ void row_begin(int, bool) { rs = alpha * pf_rs; }
   __device__ __forceinline__ void chunk(const float* acc, int col0, int lcol0, const float* s_epi,
                                         int row, bool ok) {
     if (!ok) return;

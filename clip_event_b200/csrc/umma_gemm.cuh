@@ -199,15 +199,32 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     const int et2 = (warp - 4) * 32 + lane;  // 0..255 among the epilogue threads
     constexpr int kChunksPerHalf = BN / 64;
     int acc_stage = 0; uint32_t acc_phase = 0;
+    // Per-tile scalars (column scales, row scale / LSE / label) are fetched one tile AHEAD so their
+    // global-load latency hides behind the current tile's chunk loop; the column data is double
+    // buffered in shared memory, so one 256-thread barrier per tile is enough.
+    epi.init();
+    if ((int)blockIdx.x < num_items) {
+      const int tile = (int)blockIdx.x % num_tiles;
+      const int m_blk = tile % gs.num_m_blk, n_blk = tile / gs.num_m_blk;
+      epi.prefetch(n_blk, et2, m_blk * kBM + et, m_blk * kBM + et < gs.M);
+    }
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int tile = item % num_tiles, ksp = item / num_tiles;
       const int m_blk = tile % gs.num_m_blk, n_blk = tile / gs.num_m_blk;
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's s_epi fully consumed
-      epi.tile_begin(s_epi, m_blk, n_blk, et2);
+      float* se = s_epi + acc_stage * (2 * BN);
+      epi.tile_begin(se, et2);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int row = m_blk * kBM + et;
       const bool row_ok = row < gs.M;
       epi.row_begin(row, row_ok);
+      {
+        const int nitem = item + gridDim.x;
+        if (nitem < num_items) {
+          const int ntile = nitem % num_tiles;
+          const int nm = ntile % gs.num_m_blk, nn = ntile / gs.num_m_blk;
+          epi.prefetch(nn, et2, nm * kBM + et, nm * kBM + et < gs.M);
+        }
+      }
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_stage * BN;
@@ -216,12 +233,12 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
         float acc[32];
         tmem_ld32(taddr + c * 32, acc);
         tmem_ld_wait();
-        epi.chunk(acc, n_blk * BN + c * 32, c * 32, s_epi, row, row_ok);
+        epi.chunk(acc, n_blk * BN + c * 32, c * 32, se, row, row_ok);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc_stage]);
-      epi.row_end(row, row_ok, m_blk, n_blk, ksp, s_epi, et, half);
+      epi.row_end(row, row_ok, m_blk, n_blk, ksp, se, et, half);
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   }
