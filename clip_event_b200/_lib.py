@@ -40,6 +40,7 @@ SIGNATURES = {
     "ce_scale_inplace": (_i, [_vp, _i64, _i64, _i64, _i, _vp, _vp]),
     "ce_debug_launch_count": (C.c_ulonglong, []),
     "ce_debug_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ce_debug_gemm_pair": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

@@ -869,6 +869,30 @@ GemmOperand operand(const void* raw, void* const* parts, int rows, int64_t ld, i
   return o;
 }
 
+// CTA-pair (cta_group::2) main loop for the bf16 GEMMs: two SMs share one 256 x 256 tile and each
+// stages half of the B operand, which lifts the shared-memory bandwidth limit of the 128 x 256
+// single-SM tile.  Measured at c3: the long-K plain GEMMs gain 8-10 %, the K = D GEMMs with fused
+// softmax epilogues lose 5 % (the leader's MMA issue now waits for the slower of two epilogues), so
+// only the plain GEMMs use pairs by default; CE_GEMM_PAIR (bit 0 statistics, bit 1 gradient, bit 2
+// plain GEMMs) is a tuning aid.
+inline int pair_mask() {
+  static const int mask = [] {
+    const char* e = getenv("CE_GEMM_PAIR");
+    return e != nullptr ? atoi(e) : 4;
+  }();
+  return mask;
+}
+template <bool TF, int BN, class Epi>
+int launch_gemm_auto(int kind_bit, const GemmOperand& A, const GemmOperand& B, int K,
+                     const typename Epi::Params& ep, cudaStream_t st) {
+  if constexpr (!TF && BN == 256) {
+    const int units = ((A.rows + 2 * kBM - 1) / (2 * kBM)) * ((B.rows + BN - 1) / BN);
+    if ((pair_mask() & kind_bit) != 0 && units >= num_sms())
+      return launch_gemm<TF, BN, Epi, 2>(A, B, K, 1, ep, st);
+  }
+  return launch_gemm<TF, BN, Epi, 1>(A, B, K, 1, ep, st);
+}
+
 template <int DT>
 int fwd_partial_impl(const void* img, const void* txt, const float* ls, const void* labels_i_v,
                      const int64_t* labels_t, const int64_t* index_pos, int R, int C, int P, int D,
@@ -898,7 +922,7 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
   GemmOperand op = operand<DT>(w.pos_p[0], w.pos_p, P, D, 0);
   if (mode == 0) {
     typename EpiStats<BN>::Params ep{w.rinv_i, w.rinv_t, ls, w.part_i, R, C, w.nblk_i, w.lab_local, w.lab_logit_i};
-    CE_TRY((launch_gemm<TF, BN, EpiStats<BN>>(oi, ot, D, 1, ep, st)));
+    CE_TRY((launch_gemm_auto<TF, BN, EpiStats<BN>>(1, oi, ot, D, ep, st)));
   } else {
     InstArgs ia{};
     ia.img = img; ia.txt = txt; ia.logit_scale = ls; ia.labels = labels_i_v; ia.rinv_i = w.rinv_i;
@@ -909,7 +933,7 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
   }
   {
     typename EpiStats<BN>::Params ep{w.rinv_p, w.rinv_i, ls, w.part_t, P, R, w.nblk_t, w.lab_t, w.lab_logit_t};
-    CE_TRY((launch_gemm<TF, BN, EpiStats<BN>>(op, oi, D, 1, ep, st)));
+    CE_TRY((launch_gemm_auto<TF, BN, EpiStats<BN>>(1, op, oi, D, ep, st)));
   }
   ItemArgs ia{img, txt, ls, labels_i, labels_t, index_pos, w.rinv_i, w.rinv_t, w.part_i, 2 * w.nblk_i,
               w.part_t, 2 * w.nblk_t, R, C, P, D, col_offset, reinterpret_cast<float4*>(row_part),
@@ -925,18 +949,19 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
 // C[M,N] fp32 = alpha * rowscale * (A B^t) with split-K when the tile count cannot fill the GPU.
 // C[M,N] fp32 = alpha * rowscale * (A B^t).  Narrow tiles when the wide ones cannot fill the GPU,
 // split-K (red.add into a zeroed buffer) only when even those cannot.  `accumulate`: add into `out`.
-template <bool TF, int BN>
+template <bool TF, int BN, int CG = 1>
 int plain_gemm_bn(const GemmOperand& A, const GemmOperand& B, int K, float* out, int64_t ldo,
                   const float* rowscale, const float* ls, bool accumulate, cudaStream_t st) {
   using Cfg = GemmCfg<TF, BN>;
-  int tiles = ((A.rows + kBM - 1) / kBM) * ((B.rows + BN - 1) / BN);
+  const int workers = num_sms() / CG;
+  int tiles = ((A.rows + kBM * CG - 1) / (kBM * CG)) * ((B.rows + BN - 1) / BN);
   int kblk = (K + Cfg::kBK - 1) / Cfg::kBK;
   int splits = 1;
-  if (tiles * 2 <= num_sms()) splits = std::max(1, std::min({num_sms() / tiles, kblk / 8, 16}));
+  if (tiles * 2 <= workers) splits = std::max(1, std::min({workers / tiles, kblk / 8, 16}));
   if (splits > 1 && !accumulate) CE_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)A.rows * ldo, st));
   // accumulate with red.add: a read-modify-write of the thread-per-row tile is 4x slower (measured)
   typename EpiStore<BN>::Params ep{out, ldo, rowscale, nullptr, ls, (splits > 1 || accumulate) ? 1 : 0, A.rows, B.rows};
-  return launch_gemm<TF, BN, EpiStore<BN>>(A, B, K, splits, ep, st);
+  return launch_gemm<TF, BN, EpiStore<BN>, CG>(A, B, K, splits, ep, st);
 }
 template <bool TF>
 int plain_gemm(const GemmOperand& A, const GemmOperand& B, int K, float* out, int64_t ldo,
@@ -946,7 +971,11 @@ int plain_gemm(const GemmOperand& A, const GemmOperand& B, int K, float* out, in
   } else {
     // wide tiles unless they leave most SMs idle AND the reduction is too short to split
     int wide = ((A.rows + kBM - 1) / kBM) * ((B.rows + 255) / 256);
-    if (wide * 2 > num_sms() || K >= 16384) return plain_gemm_bn<false, 256>(A, B, K, out, ldo, rowscale, ls, accumulate, st);
+    if (wide * 2 > num_sms() || K >= 16384) {
+      if ((pair_mask() & 4) != 0 && wide >= 32)
+        return plain_gemm_bn<false, 256, 2>(A, B, K, out, ldo, rowscale, ls, accumulate, st);
+      return plain_gemm_bn<false, 256>(A, B, K, out, ldo, rowscale, ls, accumulate, st);
+    }
     return plain_gemm_bn<false, 128>(A, B, K, out, ldo, rowscale, ls, accumulate, st);
   }
 }
@@ -970,7 +999,7 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     ep.rinv_row = w.rinv_i; ep.rinv_col = w.rinv_t; ep.logit_scale = ls; ep.lse2_row = w.lse2_row;
     ep.lab_row = w.lab_local; ep.g = g_i; ep.inv_count = 1.f / (float)R_total;
     ep.G0 = w.G[0]; ep.G1 = w.G[1]; ep.ldg = w.ldg; ep.dls_part = w.dls_part; ep.M = R; ep.N = C;
-    CE_TRY((launch_gemm<TF, BN, EpiGrad<BN, TF>>(oi, ot, D, 1, ep, st)));
+    CE_TRY((launch_gemm_auto<TF, BN, EpiGrad<BN, TF>>(2, oi, ot, D, ep, st)));
   } else {          // over-instance image side: direct kernel, writes d I^ (local rows) and d T^
     CE_CUDA_TRY(cudaMemsetAsync(w.dls_part, 0, sizeof(float) * (size_t)w.tiles_g * 8, st));
     CE_CUDA_TRY(cudaMemsetAsync(dimg_hat_part, 0, sizeof(float) * (size_t)R * D, st));
@@ -989,7 +1018,7 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     ep.lab_row = w.lab_t; ep.g = g_t; ep.inv_count = 1.f / (float)P_total;
     ep.G0 = w.Gt[0]; ep.G1 = w.Gt[1]; ep.ldg = w.ldgt; ep.dls_part = w.dls_part + (size_t)w.tiles_g * 8;
     ep.M = P; ep.N = R;
-    CE_TRY((launch_gemm<TF, BN, EpiGrad<BN, TF>>(op, oi, D, 1, ep, st)));
+    CE_TRY((launch_gemm_auto<TF, BN, EpiGrad<BN, TF>>(2, op, oi, D, ep, st)));
   }
   sum_dls_kernel<<<1, 1024, 0, st>>>(w.dls_part, n_dls, dls_out);
   CE_LAUNCH_CHECK();
@@ -1178,4 +1207,17 @@ extern "C" int ce_debug_gemm(const void* A, const void* B, float* C, int M, int 
   }
   EpiStore<256>::Params ep{C, N, nullptr, nullptr, nullptr, split_k > 1 ? 1 : 0, M, N};
   return launch_gemm<false, 256, EpiStore<256>>(oa, ob, K, split_k, ep, st);
+}
+
+extern "C" int ce_debug_gemm_pair(const void* A, const void* B, float* C, int M, int N, int K, int dtype,
+                                  int a_mn_major, int b_mn_major, int split_k, ce_stream_t stream) {
+  CE_TRY(check_device());
+  if (dtype != CE_BF16) return fail(CE_ERR_DTYPE, "debug_gemm_pair: bf16 only");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GemmOperand oa{}, ob{};
+  oa.ptr[0] = A; oa.ptr[1] = A; oa.rows = M; oa.ld = a_mn_major ? M : K; oa.mn_major = a_mn_major;
+  ob.ptr[0] = B; ob.ptr[1] = B; ob.rows = N; ob.ld = b_mn_major ? N : K; ob.mn_major = b_mn_major;
+  if (split_k > 1) CE_CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+  EpiStore<256>::Params ep{C, N, nullptr, nullptr, nullptr, split_k > 1 ? 1 : 0, M, N};
+  return launch_gemm<false, 256, EpiStore<256>, 2>(oa, ob, K, split_k, ep, st);
 }

@@ -17,6 +17,8 @@
 // gradient, or plain scaled store / split-K accumulate.
 #pragma once
 
+#include <stdlib.h>
+
 #include "ce_common.cuh"
 
 namespace ce {
@@ -35,23 +37,29 @@ struct GemmShape {
   int a_mn, b_mn;          // operand majorness: 0 = K-major, 1 = MN-major
 };
 
-template <bool TF32X3, int BN, int EPI_STAGE = 0>   // EPI_STAGE: bytes of epilogue staging smem
+// EPI_STAGE: bytes of epilogue staging smem.  CG: CTAs per tile group -- 1, or 2 = a CTA pair on one
+// 256 x BN tile (`cta_group::2`): each CTA stages its 128 rows of A and HALF of the B tile, so the
+// shared-memory traffic per flop halves.
+template <bool TF32X3, int BN, int EPI_STAGE = 0, int CG = 1>
 struct GemmCfg {
   static constexpr int kElemBytes = TF32X3 ? 4 : 2;
   static constexpr int kBK = kSwizzleBytes / kElemBytes;     // elements of K per stage: 32 / 64
   static constexpr int kUmmaK = 32 / kElemBytes;             // K per instruction: 8 / 16
   static constexpr int kParts = TF32X3 ? 2 : 1;              // hi, lo
   static constexpr int kABytes = kBM * kSwizzleBytes;        // one A part per stage
-  static constexpr int kBBytes = BN * kSwizzleBytes;
+  static constexpr int kBRows = BN / CG;                     // rows of the B tile staged by one CTA
+  static constexpr int kBBytes = kBRows * kSwizzleBytes;
   static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
   static constexpr int kBudget = 216 * 1024 - EPI_STAGE;
-  static constexpr int kStages = kBudget / kStageBytes > 6 ? 6 : kBudget / kStageBytes;
+  static constexpr int kMaxStages = CG == 2 ? 8 : 6;
+  static constexpr int kStages = kBudget / kStageBytes > kMaxStages ? kMaxStages : kBudget / kStageBytes;
   static constexpr int kEpiStageBytes = EPI_STAGE;
   static constexpr int kTmemCols = 2 * BN;                   // double-buffered accumulator
   static constexpr int kEpiFloats = 4 * BN;                  // per-tile column data for the epilogue
   static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes +
                                        sizeof(float) * kEpiFloats + 256 /*barriers*/ + EPI_STAGE;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
+  static_assert(CG == 1 || (CG == 2 && !TF32X3), "CTA pairs are wired for the bf16 path only");
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns");
 };
 
@@ -68,10 +76,10 @@ struct TmapSet {
 //     __device__ void row_end(int row, bool row_ok, int m_blk, int n_blk, int k_split, float* s_epi, int et);
 //   };
 
-template <bool TF32X3, int BN, class Epi>
+template <bool TF32X3, int BN, class Epi, int CG = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const typename Epi::Params ep) {
-  using Cfg = GemmCfg<TF32X3, BN, Epi::kStageBytesPerWarp * 8>;
+  using Cfg = GemmCfg<TF32X3, BN, Epi::kStageBytesPerWarp * 8, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -85,7 +93,12 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
   uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;   // [8 warps][kStageBytesPerWarp]
 
   const int warp = warp_id(), lane = lane_id();
-  const int num_tiles = gs.num_m_blk * gs.num_n_blk;
+  // CG == 2: CTAs 2w and 2w+1 form worker w; CTA rank r owns rows [(2*unit + r) * 128, +128) of the
+  // 256-row unit and stages columns [r * BN/2, +BN/2) of the B tile.  Rank 0 (the leader) issues the MMAs.
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int worker = (int)blockIdx.x / CG, num_workers = (int)gridDim.x / CG;
+  const int num_m_units = (gs.num_m_blk + CG - 1) / CG;
+  const int num_tiles = num_m_units * gs.num_n_blk;
   const int num_items = num_tiles * gs.k_splits;
 
   if (warp == 0 && lane == 0) {
@@ -94,55 +107,79 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     if (TF32X3) { tma_prefetch_desc(&tm.a[1]); tma_prefetch_desc(&tm.b[1]); }
   }
   if (warp == 1 && lane == 0) {
+    // pair mode: the leader's full barrier collects the TMA bytes of both CTAs (one local expect_tx
+    // for the pair's bytes), its accumulator-empty barrier the epilogue warps of both CTAs
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8 * CG); }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers must exist before anything lands on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
     // ================= TMA producer =================
     int stage = 0; uint32_t phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    // pair mode: completion is signalled on the LEADER's full barrier (a shared::cluster address)
+    auto load = [&](void* dst, const CUtensorMap* m, int st_idx, int c0, int c1) {
+      if constexpr (CG == 2) tma_load_2d_pair(dst, m, map_to_cta(&full_bar[st_idx], 0), c0, c1);
+      else tma_load_2d(dst, m, &full_bar[st_idx], c0, c1);
+    };
+    for (int item = worker; item < num_items; item += num_workers) {
       const int tile = item % num_tiles, ksp = item / num_tiles;
-      const int m_blk = tile % gs.num_m_blk, n_blk = tile / gs.num_m_blk;
+      const int m_blk = (tile % num_m_units) * CG + (int)cta_rank, n_blk = tile / num_m_units;
+      const int n0 = n_blk * BN + (int)cta_rank * Cfg::kBRows;   // first B row this CTA stages
       const int kb0 = ksp * gs.kblk_per_split;
       const int kb1 = min(kb0 + gs.kblk_per_split, gs.kblk_total);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = stage_base + (size_t)stage * Cfg::kStageBytes;
-        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        // The peer never arrives on the leader's barrier: its bytes may land before the leader's
+        // expect_tx (the transaction count goes negative for a moment), but the phase cannot
+        // complete until the leader's arrival, and the peer cannot run a phase ahead because its
+        // own empty barrier is released by the leader's commit.
+        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
 #pragma unroll
         for (int part = 0; part < Cfg::kParts; ++part) {
           uint8_t* sa = st + part * Cfg::kABytes;
           uint8_t* sb = st + Cfg::kParts * Cfg::kABytes + part * Cfg::kBBytes;
           if (!gs.a_mn) {
-            tma_load_2d(sa, &tm.a[part], &full_bar[stage], kb * Cfg::kBK, m_blk * kBM);
+            load(sa, &tm.a[part], stage, kb * Cfg::kBK, m_blk * kBM);
           } else {  // [K, M] row-major: boxes of (kBK rows of K) x (one 128-byte run of M)
 #pragma unroll
             for (int c = 0; c < kBM / Cfg::kBK; ++c)
-              tma_load_2d(sa + c * Cfg::kBK * kSwizzleBytes, &tm.a[part], &full_bar[stage],
-                          m_blk * kBM + c * Cfg::kBK, kb * Cfg::kBK);
+              load(sa + c * Cfg::kBK * kSwizzleBytes, &tm.a[part], stage, m_blk * kBM + c * Cfg::kBK,
+                   kb * Cfg::kBK);
           }
           if (!gs.b_mn) {
-            tma_load_2d(sb, &tm.b[part], &full_bar[stage], kb * Cfg::kBK, n_blk * BN);
+            load(sb, &tm.b[part], stage, kb * Cfg::kBK, n0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / Cfg::kBK; ++c)
-              tma_load_2d(sb + c * Cfg::kBK * kSwizzleBytes, &tm.b[part], &full_bar[stage],
-                          n_blk * BN + c * Cfg::kBK, kb * Cfg::kBK);
+            for (int c = 0; c < Cfg::kBRows / Cfg::kBK; ++c)
+              load(sb + c * Cfg::kBK * kSwizzleBytes, &tm.b[part], stage, n0 + c * Cfg::kBK,
+                   kb * Cfg::kBK);
           }
         }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ================= MMA issuer =================
-    const uint32_t idesc = umma_idesc(TF32X3, kBM, BN, gs.a_mn != 0, gs.b_mn != 0);
+    if constexpr (CG == 2) {
+      // drain: every multicast commit aimed at this CTA's empty barriers must have landed before the
+      // CTA may exit
+      for (int i = 0; i < Cfg::kStages; ++i) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+    // ================= MMA issuer (pair mode: the leader CTA only) =================
+    const uint32_t idesc = umma_idesc(TF32X3, kBM * CG, BN, gs.a_mn != 0, gs.b_mn != 0);
     // K-major: 8-row groups 1024 B apart, K advances 32 B inside the swizzle atom.
     // MN-major: 8-K-row groups 1024 B apart, 128-byte MN runs kBK*128 B apart, K advances by rows.
     const uint32_t a_lbo = gs.a_mn ? Cfg::kBK * kSwizzleBytes : 16, b_lbo = gs.b_mn ? Cfg::kBK * kSwizzleBytes : 16;
@@ -154,7 +191,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     const uint32_t a_sbo = (TF32X3 && gs.a_mn) ? 512u : 1024u, b_sbo = (TF32X3 && gs.b_mn) ? 512u : 1024u;
     int stage = 0; uint32_t phase = 0;
     int acc_stage = 0; uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (int item = worker; item < num_items; item += num_workers) {
       const int ksp = item / num_tiles;
       const int kb0 = ksp * gs.kblk_per_split;
       const int kb1 = min(kb0 + gs.kblk_per_split, gs.kblk_total);
@@ -178,14 +215,20 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
             umma<true>(tmem_d, da_lo, db_hi, idesc, first);
             umma<true>(tmem_d, da_hi, db_lo, idesc, 1u);
             umma<true>(tmem_d, da_hi, db_hi, idesc, 1u);
+          } else if constexpr (CG == 2) {
+            umma_pair_bf16(tmem_d, da_hi, db_hi, idesc, first);
           } else {
             umma<false>(tmem_d, da_hi, db_hi, idesc, first);
           }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+        // frees the smem stage (in both CTAs of a pair) once these MMAs retire
+        if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 3);
+        else umma_commit(&empty_bar[stage]);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tfull_bar[acc_stage]);  // accumulator ready for the epilogue
+      // accumulator ready for the epilogue
+      if constexpr (CG == 2) umma_commit_pair(&tfull_bar[acc_stage], 3);
+      else umma_commit(&tfull_bar[acc_stage]);
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -203,14 +246,15 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     // global-load latency hides behind the current tile's chunk loop; the column data is double
     // buffered in shared memory, so one 256-thread barrier per tile is enough.
     epi.init();
-    if ((int)blockIdx.x < num_items) {
-      const int tile = (int)blockIdx.x % num_tiles;
-      const int m_blk = tile % gs.num_m_blk, n_blk = tile / gs.num_m_blk;
+    if (worker < num_items) {
+      const int tile = worker % num_tiles;
+      const int m_blk = (tile % num_m_units) * CG + (int)cta_rank, n_blk = tile / num_m_units;
       epi.prefetch(n_blk, et2, m_blk * kBM + et, m_blk * kBM + et < gs.M);
     }
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (int item = worker; item < num_items; item += num_workers) {
       const int tile = item % num_tiles, ksp = item / num_tiles;
-      const int m_blk = tile % gs.num_m_blk, n_blk = tile / gs.num_m_blk;
+      const int m_blk = (tile % num_m_units) * CG + (int)cta_rank, n_blk = tile / num_m_units;
+      const bool tile_ok = CG == 1 || m_blk < gs.num_m_blk;   // odd row-block count: the peer idles
       float* se = s_epi + acc_stage * (2 * BN);
       epi.tile_begin(se, et2);
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -218,34 +262,44 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       const bool row_ok = row < gs.M;
       epi.row_begin(row, row_ok);
       {
-        const int nitem = item + gridDim.x;
+        const int nitem = item + num_workers;
         if (nitem < num_items) {
           const int ntile = nitem % num_tiles;
-          const int nm = ntile % gs.num_m_blk, nn = ntile / gs.num_m_blk;
+          const int nm = (ntile % num_m_units) * CG + (int)cta_rank, nn = ntile / num_m_units;
           epi.prefetch(nn, et2, nm * kBM + et, nm * kBM + et < gs.M);
         }
       }
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_stage * BN;
+      if (tile_ok) {
 #pragma unroll 1
-      for (int c = half * kChunksPerHalf; c < (half + 1) * kChunksPerHalf; ++c) {
-        float acc[32];
-        tmem_ld32(taddr + c * 32, acc);
-        tmem_ld_wait();
-        epi.chunk(acc, n_blk * BN + c * 32, c * 32, se, row, row_ok);
+        for (int c = half * kChunksPerHalf; c < (half + 1) * kChunksPerHalf; ++c) {
+          float acc[32];
+          tmem_ld32(taddr + c * 32, acc);
+          tmem_ld_wait();
+          epi.chunk(acc, n_blk * BN + c * 32, c * 32, se, row, row_ok);
+        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc_stage]);
-      epi.row_end(row, row_ok, m_blk, n_blk, ksp, se, et, half);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(map_to_cta(&tempty_bar[acc_stage], 0));
+        else mbar_arrive(&tempty_bar[acc_stage]);
+      }
+      if (tile_ok) epi.row_end(row, row_ok, m_blk, n_blk, ksp, se, et, half);
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if constexpr (CG == 2) {
+    cluster_sync_all();   // neither CTA may release TMEM or exit while its peer still uses the pair
+    if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -263,10 +317,10 @@ struct GemmOperand {
   int mn_major;        // 0: [rows, K] row-major; 1: [K, rows] row-major
 };
 
-template <bool TF32X3, int BN>
+template <bool TF32X3, int BN, int CG = 1>
 int build_tmaps(TmapSet* tm, GemmShape* gs, const GemmOperand& A, const GemmOperand& B, int K,
                 int k_splits) {
-  using Cfg = GemmCfg<TF32X3, BN>;
+  using Cfg = GemmCfg<TF32X3, BN, 0, CG>;
   gs->M = A.rows; gs->N = B.rows; gs->K = K;
   gs->num_m_blk = (A.rows + kBM - 1) / kBM;
   gs->num_n_blk = (B.rows + BN - 1) / BN;
@@ -279,27 +333,54 @@ int build_tmaps(TmapSet* tm, GemmShape* gs, const GemmOperand& A, const GemmOper
   for (int part = 0; part < Cfg::kParts; ++part) {
     if (!A.mn_major) CE_TRY(make_tmap(&tm->a[part], A.ptr[part], TF32X3, K, A.rows, A.ld, Cfg::kBK, kBM));
     else CE_TRY(make_tmap(&tm->a[part], A.ptr[part], TF32X3, A.rows, K, A.ld, Cfg::kBK, Cfg::kBK, TF32X3));
-    if (!B.mn_major) CE_TRY(make_tmap(&tm->b[part], B.ptr[part], TF32X3, K, B.rows, B.ld, Cfg::kBK, BN));
+    if (!B.mn_major) CE_TRY(make_tmap(&tm->b[part], B.ptr[part], TF32X3, K, B.rows, B.ld, Cfg::kBK, Cfg::kBRows));
     else CE_TRY(make_tmap(&tm->b[part], B.ptr[part], TF32X3, B.rows, K, B.ld, Cfg::kBK, Cfg::kBK, TF32X3));
   }
   if (Cfg::kParts == 1) { tm->a[1] = tm->a[0]; tm->b[1] = tm->b[0]; }
   return CE_OK;
 }
 
-template <bool TF32X3, int BN, class Epi>
+template <bool TF32X3, int BN, class Epi, int CG = 1>
 int launch_gemm(const GemmOperand& A, const GemmOperand& B, int K, int k_splits,
                 const typename Epi::Params& ep, cudaStream_t st, int* items_out = nullptr) {
-  using Cfg = GemmCfg<TF32X3, BN, Epi::kStageBytesPerWarp * 8>;
+  using Cfg = GemmCfg<TF32X3, BN, Epi::kStageBytesPerWarp * 8, CG>;
   TmapSet tm;
   GemmShape gs;
-  CE_TRY((build_tmaps<TF32X3, BN>(&tm, &gs, A, B, K, k_splits)));
-  const int items = gs.num_m_blk * gs.num_n_blk * gs.k_splits;
+  CE_TRY((build_tmaps<TF32X3, BN, CG>(&tm, &gs, A, B, K, k_splits)));
+  const int items = (gs.num_m_blk + CG - 1) / CG * gs.num_n_blk * gs.k_splits;
   if (items_out) *items_out = items;
   if (items == 0) return CE_OK;
-  auto kern = umma_gemm_kernel<TF32X3, BN, Epi>;
+  auto kern = umma_gemm_kernel<TF32X3, BN, Epi, CG>;
   CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
-  int grid = items < num_sms() ? items : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tm, gs, ep);
+  if constexpr (CG == 1) {
+    const int workers = items < num_sms() ? items : num_sms();
+    kern<<<workers, kGemmThreads, Cfg::kSmemBytes, st>>>(tm, gs, ep);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms() / CG * CG);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // A persistent kernel must be fully co-resident: GPCs with an odd number of usable SMs leave
+    // fewer than num_sms/2 slots for CTA pairs, and a pair that waits for a second wave would
+    // serialise its whole share of the work.
+    static thread_local int max_pairs = 0;
+    if (max_pairs == 0) {
+      int n = 0;
+      CE_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      if (n < 1) return fail(CE_ERR_ARCH, "no CTA pair of the GEMM kernel fits on this device");
+      max_pairs = n;
+      if (getenv("CE_DEBUG")) fprintf(stderr, "clip_event_b200: %d co-resident CTA pairs\n", n);
+    }
+    const int workers = items < max_pairs ? items : max_pairs;
+    cfg.gridDim = dim3(workers * CG);
+    CE_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, gs, ep));
+  }
   CE_LAUNCH_CHECK();
   return CE_OK;
 }

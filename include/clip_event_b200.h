@@ -199,6 +199,11 @@ unsigned long long ce_debug_launch_count(void);
 int ce_debug_gemm(const void* A, const void* B, float* C, int M, int N, int K, int dtype,
                   int a_mn_major, int b_mn_major, int split_k, ce_stream_t stream);
 
+/* Same contract, CE_BF16 only, through the CTA-pair main loop (`tcgen05.mma.cta_group::2`: two SMs
+ * on one 256 x 256 tile, each staging its 128 rows of A and half of the B tile). */
+int ce_debug_gemm_pair(const void* A, const void* B, float* C, int M, int N, int K, int dtype,
+                       int a_mn_major, int b_mn_major, int split_k, ce_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

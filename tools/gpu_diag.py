@@ -10,7 +10,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["gemm_bf16_kk", "gemm_bf16_mn", "gemm_f32", "ot_blocks", "ot_fused", "contrastive", "similarity"]
+GROUPS = ["gemm_bf16_kk", "gemm_bf16_mn", "gemm_pair", "gemm_f32", "ot_blocks", "ot_fused", "contrastive", "similarity"]
 
 
 def rel(a, b):
@@ -20,7 +20,7 @@ def rel(a, b):
     return (a - b).norm().item() / (d if d > 0 else 1.0)
 
 
-def run_gemm(dtype_name, cases):
+def run_gemm(dtype_name, cases, pair=False):
     import torch
     from clip_event_b200 import _lib as L
     lib = L.load()
@@ -36,14 +36,15 @@ def run_gemm(dtype_name, cases):
         Ad = (A.t().contiguous() if amn else A).to(dt).cuda()
         Bd = (B.t().contiguous() if bmn else B).to(dt).cuda()
         Cd = torch.full((M, N), float("nan"), device="cuda")
-        rc = lib.ce_debug_gemm(Ad.data_ptr(), Bd.data_ptr(), Cd.data_ptr(), M, N, K, code, amn, bmn, sk,
+        fn = lib.ce_debug_gemm_pair if pair else lib.ce_debug_gemm
+        rc = fn(Ad.data_ptr(), Bd.data_ptr(), Cd.data_ptr(), M, N, K, code, amn, bmn, sk,
                                torch.cuda.current_stream().cuda_stream)
         msg = "" if rc == 0 else L.last_error()
         torch.cuda.synchronize()
         out = Cd.cpu()
         bad = (out != ref) | out.isnan()
         nbad = int(bad.sum())
-        line = "gemm %s M=%d N=%d K=%d a_mn=%d b_mn=%d sk=%d rc=%d bad=%d/%d maxerr=%.3g %s" % (
+        line = ("pair " if pair else "") + "gemm %s M=%d N=%d K=%d a_mn=%d b_mn=%d sk=%d rc=%d bad=%d/%d maxerr=%.3g %s" % (
             dtype_name, M, N, K, amn, bmn, sk, rc, nbad, M * N, float((out - ref).abs().nan_to_num(1e9).max()), msg)
         print(line, flush=True)
         if nbad:
@@ -65,6 +66,15 @@ def group_gemm_bf16_mn():
     run_gemm("bf16", [(128, 256, 64, 1, 0, 1), (128, 256, 64, 0, 1, 1), (128, 256, 64, 1, 1, 1),
                       (256, 512, 256, 1, 1, 1), (520, 512, 1000, 0, 1, 1), (2304, 512, 256, 1, 1, 1),
                       (2304, 512, 1024, 1, 1, 3)])
+
+
+def group_gemm_pair():
+    run_gemm("bf16", [(256, 256, 64, 0, 0, 1), (256, 256, 512, 0, 0, 1), (128, 256, 128, 0, 0, 1),
+                      (512, 512, 512, 0, 0, 1), (100, 200, 72, 0, 0, 1), (1024, 2304, 512, 0, 0, 1),
+                      (4096, 4608, 512, 0, 0, 1), (256, 256, 2048, 0, 0, 4),
+                      (256, 256, 64, 1, 0, 1), (256, 256, 64, 0, 1, 1), (256, 256, 64, 1, 1, 1),
+                      (520, 512, 1000, 0, 1, 1), (2304, 512, 256, 1, 1, 1), (2304, 512, 1024, 1, 1, 3),
+                      (4608, 512, 4096, 1, 1, 1), (4096, 512, 4608, 0, 1, 1)], pair=True)
 
 
 def group_gemm_f32():
