@@ -42,7 +42,9 @@ struct EpiStats {
   };
   static constexpr int kStageBytesPerWarp = 0;
   uint8_t* stage;
+  const CUtensorMap* out_map;
   Params p;
+  __device__ __forceinline__ void finish() {}
   float kk, rinv_r, m2, l;
   int lab;
   bool fixed_ref;
@@ -134,11 +136,19 @@ struct EpiGrad {
   // G = g' * t ; dls' += g' * v.   Here kr = s*log2e/|row|, cs = coef/(s*log2e), so that
   // g'*t = coef*softmax/(|row||col|) and sum(g*L) = s*log2e*ln2 * sum(g'*(v + lse)); the lse part
   // vanishes because a softmax-minus-one-hot row sums to zero.
-  // bf16: the warp's [32 rows x BN/2 columns] are staged in shared memory and written out with
-  // fully coalesced 16-byte stores (thread-per-row stores touch 32 half-filled sectors each).
-  static constexpr int kRowBytes = (BN / 2) * 2 + 16;
-  static constexpr int kStageBytesPerWarp = TF32X3 ? 0 : 32 * kRowBytes;
+  // bf16: the warp's [32 rows x BN/2 columns] are staged in shared memory as 128-byte-swizzled
+  // [32 x 64] boxes and written out by TMA (thread-per-row global stores touch 32 half-filled
+  // sectors each, and a copy-out loop costs the epilogue a quarter of its issue slots).
+  static constexpr int kBoxes = (BN / 2) / 64;
+  static constexpr int kBoxBytes = 32 * 128;
+  static constexpr int kStageBytesPerWarp = TF32X3 ? 0 : kBoxes * kBoxBytes;
   uint8_t* stage;
+  const CUtensorMap* out_map;
+  __device__ __forceinline__ void finish() {
+    if constexpr (!TF32X3) {
+      if ((threadIdx.x & 31) == 0) tma_store_wait_all();
+    }
+  }
   float sl, kr, lse2r, cs, dls, cs_all;
   int lab;
   float pf_col, pf_rinv, pf_lse;
@@ -165,6 +175,10 @@ struct EpiGrad {
     lab = pf_lab;
     cs = pf_ok ? cs_all : 0.f;
     dls = 0.f;
+    if constexpr (!TF32X3) {   // the previous tile's TMA stores must have drained the staging boxes
+      if ((threadIdx.x & 31) == 0) tma_store_wait_read();
+      __syncwarp();
+    }
   }
   __device__ __forceinline__ void chunk(const float* acc, int col0, int lcol0, const float* s_epi,
                                         int row, bool ok) {
@@ -213,8 +227,12 @@ struct EpiGrad {
       }
     }
     if constexpr (!TF32X3) {
-      // lcol0 within this warp's column half: (lcol0 % (BN/2)) columns into the staged row
-      uint8_t* dst = stage + (threadIdx.x & 31) * kRowBytes + (lcol0 % (BN / 2)) * 2;
+      // (lcol0 % (BN/2)) columns into this warp's column half: box = 64-column group, then the
+      // 16-byte slot inside the 128-byte row, XOR-swizzled with the row as SWIZZLE_128B expects
+      const int lane = threadIdx.x & 31;
+      const int cw = lcol0 % (BN / 2);
+      uint8_t* rowp = stage + (cw / 64) * kBoxBytes + lane * 128;
+      const int slot0 = (cw % 64) / 8;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 pk;
@@ -226,7 +244,7 @@ struct EpiGrad {
         pk.y = *reinterpret_cast<uint32_t*>(&t1);
         pk.z = *reinterpret_cast<uint32_t*>(&t2);
         pk.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(dst + i * 2) = pk;
+        *reinterpret_cast<uint4*>(rowp + (((slot0 + i / 8) ^ (lane & 7)) << 4)) = pk;
       }
       return;
     }
@@ -256,21 +274,17 @@ struct EpiGrad {
       p.dls_part[(int64_t)tile * 8 + half * 4 + (et >> 5)] = v;
     }
     if constexpr (!TF32X3) {
+      fence_proxy_async();   // generic-proxy writes of the boxes -> visible to the TMA (async proxy)
       __syncwarp();
       const int lane = et & 31;
-      const int row0 = row - lane;                               // first row of this warp
-      const int64_t colbase = (int64_t)n_blk * BN + half * (BN / 2);
-      constexpr int kPiecesPerRow = (BN / 2) / 8;                // 16-byte pieces (8 bf16) per staged row
-      __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(p.G0);
+      if (lane == 0) {
+        const int row0 = row;                                    // first row of this warp
+        const int colbase = n_blk * BN + half * (BN / 2);
 #pragma unroll
-      for (int it = 0; it < kPiecesPerRow; ++it) {
-        const int piece = it * 32 + lane;
-        const int r = piece / kPiecesPerRow, c = piece % kPiecesPerRow;
-        const uint4 val = *reinterpret_cast<const uint4*>(stage + r * kRowBytes + c * 16);
-        if (row0 + r < p.M && colbase + c * 8 < p.ldg)
-          *reinterpret_cast<uint4*>(G + (int64_t)(row0 + r) * p.ldg + colbase + c * 8) = val;
+        for (int b = 0; b < kBoxes; ++b)
+          if (colbase + b * 64 < (int)p.ldg) tma_store_2d(out_map, stage + b * kBoxBytes, colbase + b * 64, row0);
+        tma_store_commit();
       }
-      __syncwarp();
     }
   }
 };
@@ -288,7 +302,9 @@ struct EpiStore {
   };
   static constexpr int kStageBytesPerWarp = 0;
   uint8_t* stage;
+  const CUtensorMap* out_map;
   Params p;
+  __device__ __forceinline__ void finish() {}
   float rs, alpha, pf_col, pf_rs;
   __device__ __forceinline__ void init() {
     alpha = p.logit_scale != nullptr ? expf(__ldg(p.logit_scale)) : 1.f;
@@ -689,7 +705,7 @@ __global__ void __launch_bounds__(1024) sum_dls_kernel(const float* part, int n,
 // dx = (d - x^ (x^ . d)) / |x|, one warp per row (model_clip.py:496-497 backward).
 // `extra` (optional): per-row index into a second fp32 matrix whose row is added to d first (the
 // text-side gradient of a positive description).
-template <int DT>
+template <int DT, int kMaxIter>
 __global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, int D, void* out,
                                      const int* extra_idx, const float* extra) {
   using T = typename In<DT>::type;
@@ -701,8 +717,9 @@ __global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, 
   const float* dr = d + (int64_t)r * D;
   const int ei = extra_idx != nullptr ? extra_idx[r] : -1;
   const float* er = ei >= 0 ? extra + (int64_t)ei * D : nullptr;
-  // one pass: the row (x and d) stays in registers for D <= 32 * V * kMaxIter
-  constexpr int kMaxIter = 4;
+  // one pass: the row (x and d) stays in registers for D <= 32 * V * kMaxIter; kMaxIter is sized
+  // to the row by the launcher, because the register count decides how many rows an SM keeps in
+  // flight (92 registers at kMaxIter = 4 left the kernel at 22 % occupancy and 3 TB/s)
   float xv[kMaxIter][8], dv[kMaxIter][8];
   float n2 = 0.f, dot = 0.f;
   const bool fits = D <= 32 * V * kMaxIter;
@@ -772,6 +789,20 @@ __global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, 
       }
     }
   }
+}
+
+template <int DT>
+int launch_normalize_bwd(const void* x, const float* d, int rows, int D, void* out, const int* extra_idx,
+                         const float* extra, cudaStream_t st) {
+  const int per_iter = 32 * In<DT>::kVec;
+  const int iters = (D + per_iter - 1) / per_iter;
+  const int blocks = (int)(((int64_t)rows * 32 + 255) / 256);
+  if (iters <= 1) normalize_bwd_kernel<DT, 1><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra);
+  else if (iters == 2) normalize_bwd_kernel<DT, 2><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra);
+  else if (iters == 3) normalize_bwd_kernel<DT, 3><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra);
+  else normalize_bwd_kernel<DT, 4><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -884,13 +915,13 @@ inline int pair_mask() {
 }
 template <bool TF, int BN, class Epi>
 int launch_gemm_auto(int kind_bit, const GemmOperand& A, const GemmOperand& B, int K,
-                     const typename Epi::Params& ep, cudaStream_t st) {
+                     const typename Epi::Params& ep, cudaStream_t st, const GemmOut* out = nullptr) {
   if constexpr (!TF && BN == 256) {
     const int units = ((A.rows + 2 * kBM - 1) / (2 * kBM)) * ((B.rows + BN - 1) / BN);
     if ((pair_mask() & kind_bit) != 0 && units >= num_sms())
-      return launch_gemm<TF, BN, Epi, 2>(A, B, K, 1, ep, st);
+      return launch_gemm<TF, BN, Epi, 2>(A, B, K, 1, ep, st, nullptr, out);
   }
-  return launch_gemm<TF, BN, Epi, 1>(A, B, K, 1, ep, st);
+  return launch_gemm<TF, BN, Epi, 1>(A, B, K, 1, ep, st, nullptr, out);
 }
 
 template <int DT>
@@ -999,7 +1030,8 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     ep.rinv_row = w.rinv_i; ep.rinv_col = w.rinv_t; ep.logit_scale = ls; ep.lse2_row = w.lse2_row;
     ep.lab_row = w.lab_local; ep.g = g_i; ep.inv_count = 1.f / (float)R_total;
     ep.G0 = w.G[0]; ep.G1 = w.G[1]; ep.ldg = w.ldg; ep.dls_part = w.dls_part; ep.M = R; ep.N = C;
-    CE_TRY((launch_gemm_auto<TF, BN, EpiGrad<BN, TF>>(2, oi, ot, D, ep, st)));
+    const GemmOut go{w.G[0], R, (int)w.ldg, w.ldg};
+    CE_TRY((launch_gemm_auto<TF, BN, EpiGrad<BN, TF>>(2, oi, ot, D, ep, st, TF ? nullptr : &go)));
   } else {          // over-instance image side: direct kernel, writes d I^ (local rows) and d T^
     CE_CUDA_TRY(cudaMemsetAsync(w.dls_part, 0, sizeof(float) * (size_t)w.tiles_g * 8, st));
     CE_CUDA_TRY(cudaMemsetAsync(dimg_hat_part, 0, sizeof(float) * (size_t)R * D, st));
@@ -1018,7 +1050,8 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     ep.lab_row = w.lab_t; ep.g = g_t; ep.inv_count = 1.f / (float)P_total;
     ep.G0 = w.Gt[0]; ep.G1 = w.Gt[1]; ep.ldg = w.ldgt; ep.dls_part = w.dls_part + (size_t)w.tiles_g * 8;
     ep.M = P; ep.N = R;
-    CE_TRY((launch_gemm_auto<TF, BN, EpiGrad<BN, TF>>(2, op, oi, D, ep, st)));
+    const GemmOut go{w.Gt[0], P, (int)w.ldgt, w.ldgt};
+    CE_TRY((launch_gemm_auto<TF, BN, EpiGrad<BN, TF>>(2, op, oi, D, ep, st, TF ? nullptr : &go)));
   }
   sum_dls_kernel<<<1, 1024, 0, st>>>(w.dls_part, n_dls, dls_out);
   CE_LAUNCH_CHECK();
@@ -1033,8 +1066,7 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
   if (mode == 0)
     CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, C, w.ldg, 1), iB, R, w.dtxt_hat, D, w.norm_t, ls, false, st)));
   CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, P, w.ldgt, 0), iB, R, w.dpos_hat, D, w.norm_p, ls, false, st)));
-  normalize_bwd_kernel<DT><<<(C * 32 + 255) / 256, 256, 0, st>>>(txt, w.dtxt_hat, C, D, dtxt, w.col_pos, w.dpos_hat);
-  CE_LAUNCH_CHECK();
+  CE_TRY((launch_normalize_bwd<DT>(txt, w.dtxt_hat, C, D, dtxt, w.col_pos, w.dpos_hat, st)));
   return CE_OK;
 }
 
@@ -1118,8 +1150,9 @@ extern "C" int ce_contrastive_bwd_finish(const void* img_rows, const float* dimg
   if (rows == 0) return CE_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int blocks = (rows * 32 + 255) / 256;
-  if (dtype == CE_F32) normalize_bwd_kernel<CE_F32><<<blocks, 256, 0, st>>>(img_rows, dimg_hat_rows, rows, D, dimg_rows, nullptr, nullptr);
-  else normalize_bwd_kernel<CE_BF16><<<blocks, 256, 0, st>>>(img_rows, dimg_hat_rows, rows, D, dimg_rows, nullptr, nullptr);
+  (void)blocks;
+  if (dtype == CE_F32) CE_TRY((launch_normalize_bwd<CE_F32>(img_rows, dimg_hat_rows, rows, D, dimg_rows, nullptr, nullptr, st)));
+  else CE_TRY((launch_normalize_bwd<CE_BF16>(img_rows, dimg_hat_rows, rows, D, dimg_rows, nullptr, nullptr, st)));
   CE_LAUNCH_CHECK();
   return CE_OK;
 }

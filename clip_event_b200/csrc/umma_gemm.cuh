@@ -50,14 +50,15 @@ struct GemmCfg {
   static constexpr int kBRows = BN / CG;                     // rows of the B tile staged by one CTA
   static constexpr int kBBytes = kBRows * kSwizzleBytes;
   static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
-  static constexpr int kBudget = 216 * 1024 - EPI_STAGE;
+  static constexpr int kBudget = 215 * 1024 - EPI_STAGE;
   static constexpr int kMaxStages = CG == 2 ? 8 : 6;
   static constexpr int kStages = kBudget / kStageBytes > kMaxStages ? kMaxStages : kBudget / kStageBytes;
   static constexpr int kEpiStageBytes = EPI_STAGE;
   static constexpr int kTmemCols = 2 * BN;                   // double-buffered accumulator
   static constexpr int kEpiFloats = 4 * BN;                  // per-tile column data for the epilogue
-  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes +
-                                       sizeof(float) * kEpiFloats + 256 /*barriers*/ + EPI_STAGE;
+  static constexpr int kEpiStageOffset =
+      (kStages * kStageBytes + (int)sizeof(float) * kEpiFloats + 256 /*barriers*/ + 1023) / 1024 * 1024;
+  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kEpiStageOffset + EPI_STAGE;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(CG == 1 || (CG == 2 && !TF32X3), "CTA pairs are wired for the bf16 path only");
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns");
@@ -66,6 +67,28 @@ struct GemmCfg {
 struct TmapSet {
   CUtensorMap a[2];  // hi, lo (lo unused for bf16)
   CUtensorMap b[2];
+  CUtensorMap out;   // optional: output matrix for epilogues that store their tile with TMA
+};
+
+// Walks the work items of one worker (item, item + W, ...) without a division per tile:
+// item = ksp * num_tiles + tile, tile = nb * nmu + mu.
+struct TileWalk {
+  int nmu, num_tiles, W, w_mu, w_nb;
+  int item, tile, ksp, mu, nb;
+  __device__ __forceinline__ void init(int item0, int nmu_, int num_tiles_, int W_) {
+    nmu = nmu_; num_tiles = num_tiles_; W = W_;
+    w_nb = W / nmu; w_mu = W - w_nb * nmu;
+    item = item0; ksp = item0 / num_tiles; tile = item0 - ksp * num_tiles;
+    nb = tile / nmu; mu = tile - nb * nmu;
+  }
+  __device__ __forceinline__ void next() {
+    item += W; tile += W; mu += w_mu; nb += w_nb;
+    if (mu >= nmu) { mu -= nmu; ++nb; }
+    if (tile >= num_tiles) {   // next K split: rare, re-derive
+      do { tile -= num_tiles; ++ksp; } while (tile >= num_tiles);
+      nb = tile / nmu; mu = tile - nb * nmu;
+    }
+  }
 };
 
 // Epilogue interface:
@@ -80,8 +103,10 @@ template <bool TF32X3, int BN, class Epi, int CG = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const typename Epi::Params ep) {
   using Cfg = GemmCfg<TF32X3, BN, Epi::kStageBytesPerWarp * 8, CG>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // plain pointer arithmetic on the shared array keeps the address space known to the compiler
+  // (LDS/STS instead of generic LD/ST in the epilogues)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   float* s_epi = reinterpret_cast<float*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + Cfg::kEpiFloats);
@@ -90,7 +115,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;   // [8 warps][kStageBytesPerWarp]
+  // [8 warps][kStageBytesPerWarp], 1024-byte aligned (swizzled TMA-store source)
+  uint8_t* epi_stage = smem + Cfg::kEpiStageOffset;
 
   const int warp = warp_id(), lane = lane_id();
   // CG == 2: CTAs 2w and 2w+1 form worker w; CTA rank r owns rows [(2*unit + r) * 128, +128) of the
@@ -131,9 +157,11 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       if constexpr (CG == 2) tma_load_2d_pair(dst, m, map_to_cta(&full_bar[st_idx], 0), c0, c1);
       else tma_load_2d(dst, m, &full_bar[st_idx], c0, c1);
     };
-    for (int item = worker; item < num_items; item += num_workers) {
-      const int tile = item % num_tiles, ksp = item / num_tiles;
-      const int m_blk = (tile % num_m_units) * CG + (int)cta_rank, n_blk = tile / num_m_units;
+    TileWalk tw;
+    tw.init(worker, num_m_units, num_tiles, num_workers);
+    for (; tw.item < num_items; tw.next()) {
+      const int ksp = tw.ksp;
+      const int m_blk = tw.mu * CG + (int)cta_rank, n_blk = tw.nb;
       const int n0 = n_blk * BN + (int)cta_rank * Cfg::kBRows;   // first B row this CTA stages
       const int kb0 = ksp * gs.kblk_per_split;
       const int kb1 = min(kb0 + gs.kblk_per_split, gs.kblk_total);
@@ -191,8 +219,10 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     const uint32_t a_sbo = (TF32X3 && gs.a_mn) ? 512u : 1024u, b_sbo = (TF32X3 && gs.b_mn) ? 512u : 1024u;
     int stage = 0; uint32_t phase = 0;
     int acc_stage = 0; uint32_t acc_phase = 0;
-    for (int item = worker; item < num_items; item += num_workers) {
-      const int ksp = item / num_tiles;
+    TileWalk tw;
+    tw.init(worker, num_m_units, num_tiles, num_workers);
+    for (; tw.item < num_items; tw.next()) {
+      const int ksp = tw.ksp;
       const int kb0 = ksp * gs.kblk_per_split;
       const int kb1 = min(kb0 + gs.kblk_per_split, gs.kblk_total);
       mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
@@ -245,15 +275,18 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     // Per-tile scalars (column scales, row scale / LSE / label) are fetched one tile AHEAD so their
     // global-load latency hides behind the current tile's chunk loop; the column data is double
     // buffered in shared memory, so one 256-thread barrier per tile is enough.
+    epi.out_map = &tm.out;
     epi.init();
+    TileWalk tw, nx;
+    tw.init(worker, num_m_units, num_tiles, num_workers);
+    nx = tw;
     if (worker < num_items) {
-      const int tile = worker % num_tiles;
-      const int m_blk = (tile % num_m_units) * CG + (int)cta_rank, n_blk = tile / num_m_units;
-      epi.prefetch(n_blk, et2, m_blk * kBM + et, m_blk * kBM + et < gs.M);
+      const int m_blk = tw.mu * CG + (int)cta_rank;
+      epi.prefetch(tw.nb, et2, m_blk * kBM + et, m_blk * kBM + et < gs.M);
     }
-    for (int item = worker; item < num_items; item += num_workers) {
-      const int tile = item % num_tiles, ksp = item / num_tiles;
-      const int m_blk = (tile % num_m_units) * CG + (int)cta_rank, n_blk = tile / num_m_units;
+    for (; tw.item < num_items; tw = nx) {
+      const int ksp = tw.ksp;
+      const int m_blk = tw.mu * CG + (int)cta_rank, n_blk = tw.nb;
       const bool tile_ok = CG == 1 || m_blk < gs.num_m_blk;   // odd row-block count: the peer idles
       float* se = s_epi + acc_stage * (2 * BN);
       epi.tile_begin(se, et2);
@@ -261,13 +294,10 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       const int row = m_blk * kBM + et;
       const bool row_ok = row < gs.M;
       epi.row_begin(row, row_ok);
-      {
-        const int nitem = item + num_workers;
-        if (nitem < num_items) {
-          const int ntile = nitem % num_tiles;
-          const int nm = (ntile % num_m_units) * CG + (int)cta_rank, nn = ntile / num_m_units;
-          epi.prefetch(nn, et2, nm * kBM + et, nm * kBM + et < gs.M);
-        }
+      nx.next();
+      if (nx.item < num_items) {
+        const int nm = nx.mu * CG + (int)cta_rank;
+        epi.prefetch(nx.nb, et2, nm * kBM + et, nm * kBM + et < gs.M);
       }
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tc_fence_after();
@@ -290,6 +320,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       if (tile_ok) epi.row_end(row, row_ok, m_blk, n_blk, ksp, se, et, half);
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
+    epi.finish();
   }
 
   tc_fence_before();
@@ -340,13 +371,23 @@ int build_tmaps(TmapSet* tm, GemmShape* gs, const GemmOperand& A, const GemmOper
   return CE_OK;
 }
 
+// bf16 [rows, cols] row-major output written by the epilogue through TMA in [32 x 64] boxes
+struct GemmOut {
+  void* ptr;
+  int rows, cols;
+  int64_t ld;
+};
+
 template <bool TF32X3, int BN, class Epi, int CG = 1>
 int launch_gemm(const GemmOperand& A, const GemmOperand& B, int K, int k_splits,
-                const typename Epi::Params& ep, cudaStream_t st, int* items_out = nullptr) {
+                const typename Epi::Params& ep, cudaStream_t st, int* items_out = nullptr,
+                const GemmOut* out = nullptr) {
   using Cfg = GemmCfg<TF32X3, BN, Epi::kStageBytesPerWarp * 8, CG>;
   TmapSet tm;
   GemmShape gs;
   CE_TRY((build_tmaps<TF32X3, BN, CG>(&tm, &gs, A, B, K, k_splits)));
+  if (out != nullptr) CE_TRY(make_tmap(&tm.out, out->ptr, false, out->cols, out->rows, out->ld, 64, 32));
+  else tm.out = tm.a[0];
   const int items = (gs.num_m_blk + CG - 1) / CG * gs.num_n_blk * gs.k_splits;
   if (items_out) *items_out = items;
   if (items == 0) return CE_OK;
