@@ -40,6 +40,7 @@ def _compile(src: str) -> str:
     if os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
         return obj
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags += os.environ.get("CE_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DCE_GEMM_TRACE (tools/gemm_trace.py)
     cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(OBJ, src.replace(".cu", ".log"))

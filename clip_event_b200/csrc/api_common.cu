@@ -68,7 +68,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap(CUtensorMap* out, const void* ptr, bool fp32, uint64_t inner, uint64_t outer,
-              uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer, bool atom32) {
+              uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer, int swizzle) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(CE_ERR_ARCH, "cuTensorMapEncodeTiled is not available from this driver");
   const uint64_t esz = fp32 ? 4 : 2;
@@ -80,7 +80,8 @@ int make_tmap(CUtensorMap* out, const void* ptr, bool fp32, uint64_t inner, uint
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                  : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)

@@ -136,12 +136,14 @@ struct EpiGrad {
   // G = g' * t ; dls' += g' * v.   Here kr = s*log2e/|row|, cs = coef/(s*log2e), so that
   // g'*t = coef*softmax/(|row||col|) and sum(g*L) = s*log2e*ln2 * sum(g'*(v + lse)); the lse part
   // vanishes because a softmax-minus-one-hot row sums to zero.
-  // bf16: the warp's [32 rows x BN/2 columns] are staged in shared memory as 128-byte-swizzled
-  // [32 x 64] boxes and written out by TMA (thread-per-row global stores touch 32 half-filled
-  // sectors each, and a copy-out loop costs the epilogue a quarter of its issue slots).
-  static constexpr int kBoxes = (BN / 2) / 64;
+  // bf16: two 32-column chunks of the warp's 32 rows are staged in shared memory as one
+  // 128-byte-swizzled [32 x 64] box and written out by TMA.  Measured alternatives
+  // (tools/gemm_trace.py, cycles per 128 x 256 tile, main loop alone = 5300): thread-per-row
+  // global stores 9800 (32 half-filled sectors per instruction); a box per warp-tile 4000 but its
+  // 64 KB cost the main loop its fourth stage (TMA-latency bound, 7200 per tile); a box per chunk
+  // 5700 (fence + store issue four times per tile).
   static constexpr int kBoxBytes = 32 * 128;
-  static constexpr int kStageBytesPerWarp = TF32X3 ? 0 : kBoxes * kBoxBytes;
+  static constexpr int kStageBytesPerWarp = TF32X3 ? 0 : kBoxBytes;
   uint8_t* stage;
   const CUtensorMap* out_map;
   __device__ __forceinline__ void finish() {
@@ -175,10 +177,6 @@ struct EpiGrad {
     lab = pf_lab;
     cs = pf_ok ? cs_all : 0.f;
     dls = 0.f;
-    if constexpr (!TF32X3) {   // the previous tile's TMA stores must have drained the staging boxes
-      if ((threadIdx.x & 31) == 0) tma_store_wait_read();
-      __syncwarp();
-    }
   }
   __device__ __forceinline__ void chunk(const float* acc, int col0, int lcol0, const float* s_epi,
                                         int row, bool ok) {
@@ -227,12 +225,18 @@ struct EpiGrad {
       }
     }
     if constexpr (!TF32X3) {
-      // (lcol0 % (BN/2)) columns into this warp's column half: box = 64-column group, then the
-      // 16-byte slot inside the 128-byte row, XOR-swizzled with the row as SWIZZLE_128B expects
+      // the box row is 128 bytes = eight 16-byte slots, XOR-swizzled with the row as SWIZZLE_128B
+      // expects; even chunks fill slots 0..3 (after the previous store has drained the box), odd
+      // chunks slots 4..7 and hand the box to the TMA
       const int lane = threadIdx.x & 31;
-      const int cw = lcol0 % (BN / 2);
-      uint8_t* rowp = stage + (cw / 64) * kBoxBytes + lane * 128;
-      const int slot0 = (cw % 64) / 8;
+      const int odd = (lcol0 >> 5) & 1;
+      if (!odd) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+      uint8_t* rowp = stage + lane * 128;
+      const int sw = lane & 7;
+      const int slot0 = odd * 4;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 pk;
@@ -244,7 +248,15 @@ struct EpiGrad {
         pk.y = *reinterpret_cast<uint32_t*>(&t1);
         pk.z = *reinterpret_cast<uint32_t*>(&t2);
         pk.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(rowp + (((slot0 + i / 8) ^ (lane & 7)) << 4)) = pk;
+        *reinterpret_cast<uint4*>(rowp + (((slot0 + i / 8) ^ sw) << 4)) = pk;
+      }
+      if (odd) {
+        fence_proxy_async();   // generic-proxy writes of the box -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0 && col0 - 32 < (int)p.ldg) {
+          tma_store_2d(out_map, stage, col0 - 32, row);   // lane 0's row is the first row of the box
+          tma_store_commit();
+        }
       }
       return;
     }
@@ -272,19 +284,6 @@ struct EpiGrad {
     if ((et & 31) == 0) {
       int tile = n_blk * ((p.M + kBM - 1) / kBM) + m_blk;
       p.dls_part[(int64_t)tile * 8 + half * 4 + (et >> 5)] = v;
-    }
-    if constexpr (!TF32X3) {
-      fence_proxy_async();   // generic-proxy writes of the boxes -> visible to the TMA (async proxy)
-      __syncwarp();
-      const int lane = et & 31;
-      if (lane == 0) {
-        const int row0 = row;                                    // first row of this warp
-        const int colbase = n_blk * BN + half * (BN / 2);
-#pragma unroll
-        for (int b = 0; b < kBoxes; ++b)
-          if (colbase + b * 64 < (int)p.ldg) tma_store_2d(out_map, stage + b * kBoxBytes, colbase + b * 64, row0);
-        tma_store_commit();
-      }
     }
   }
 };

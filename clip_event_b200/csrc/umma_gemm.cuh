@@ -35,7 +35,20 @@ struct GemmShape {
   int kblk_total;          // reduction length in BLOCK_K units
   int kblk_per_split;
   int a_mn, b_mn;          // operand majorness: 0 = K-major, 1 = MN-major
+  long long* trace;        // -DCE_GEMM_TRACE builds only: per-tile clock64 stamps of CTA 0
 };
+
+// Pipeline tracing (tuning aid, compiled in with -DCE_GEMM_TRACE): CTA 0 records, per work item,
+// clock64 at the hand-over points of its producer / MMA / epilogue roles: trace[(item_seq * 4 + role) * 8 + k].
+#ifdef CE_GEMM_TRACE
+#define CE_TRACE(role, k)                                                                     \
+  do {                                                                                        \
+    if (gs.trace != nullptr && blockIdx.x == 0 && seq < 64)                                   \
+      gs.trace[(seq * 4 + (role)) * 8 + (k)] = clock64();                                     \
+  } while (0)
+#else
+#define CE_TRACE(role, k) do { } while (0)
+#endif
 
 // EPI_STAGE: bytes of epilogue staging smem.  CG: CTAs per tile group -- 1, or 2 = a CTA pair on one
 // 256 x BN tile (`cta_group::2`): each CTA stages its 128 rows of A and HALF of the B tile, so the
@@ -50,15 +63,18 @@ struct GemmCfg {
   static constexpr int kBRows = BN / CG;                     // rows of the B tile staged by one CTA
   static constexpr int kBBytes = kBRows * kSwizzleBytes;
   static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
-  static constexpr int kBudget = 215 * 1024 - EPI_STAGE;
+  static constexpr int kEpiFloats = 2 * BN;                  // per-tile column data, double buffered
+  static constexpr int kMaxSmem = 232448;                    // 227 KB opt-in limit per CTA
+  static constexpr int kBudget = kMaxSmem - EPI_STAGE - (int)sizeof(float) * kEpiFloats - 256 /*barriers*/;
   static constexpr int kMaxStages = CG == 2 ? 8 : 6;
   static constexpr int kStages = kBudget / kStageBytes > kMaxStages ? kMaxStages : kBudget / kStageBytes;
   static constexpr int kEpiStageBytes = EPI_STAGE;
   static constexpr int kTmemCols = 2 * BN;                   // double-buffered accumulator
-  static constexpr int kEpiFloats = 4 * BN;                  // per-tile column data for the epilogue
-  static constexpr int kEpiStageOffset =
-      (kStages * kStageBytes + (int)sizeof(float) * kEpiFloats + 256 /*barriers*/ + 1023) / 1024 * 1024;
-  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kEpiStageOffset + EPI_STAGE;
+  // layout: stages | epilogue staging (1024-byte aligned like the stages) | column data | barriers;
+  // no alignment slack: the dynamic shared-memory window itself is 1024-byte aligned (checked)
+  static constexpr int kEpiStageOffset = kStages * kStageBytes;
+  static constexpr int kEpiDataOffset = kEpiStageOffset + EPI_STAGE;
+  static constexpr size_t kSmemBytes = (size_t)kEpiDataOffset + sizeof(float) * kEpiFloats + 256;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(CG == 1 || (CG == 2 && !TF32X3), "CTA pairs are wired for the bf16 path only");
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns");
@@ -105,10 +121,10 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
   using Cfg = GemmCfg<TF32X3, BN, Epi::kStageBytesPerWarp * 8, CG>;
   // plain pointer arithmetic on the shared array keeps the address space known to the compiler
   // (LDS/STS instead of generic LD/ST in the epilogues)
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // swizzled TMA / UMMA tiles need 1024-byte alignment
   uint8_t* stage_base = smem;
-  float* s_epi = reinterpret_cast<float*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
+  float* s_epi = reinterpret_cast<float*>(smem + Cfg::kEpiDataOffset);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + Cfg::kEpiFloats);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
@@ -159,14 +175,16 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     };
     TileWalk tw;
     tw.init(worker, num_m_units, num_tiles, num_workers);
-    for (; tw.item < num_items; tw.next()) {
+    for (int seq = 0; tw.item < num_items; tw.next(), ++seq) {
       const int ksp = tw.ksp;
       const int m_blk = tw.mu * CG + (int)cta_rank, n_blk = tw.nb;
       const int n0 = n_blk * BN + (int)cta_rank * Cfg::kBRows;   // first B row this CTA stages
       const int kb0 = ksp * gs.kblk_per_split;
       const int kb1 = min(kb0 + gs.kblk_per_split, gs.kblk_total);
+      CE_TRACE(0, 0);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (kb == kb0) CE_TRACE(0, 1);
         uint8_t* st = stage_base + (size_t)stage * Cfg::kStageBytes;
         // The peer never arrives on the leader's barrier: its bytes may land before the leader's
         // expect_tx (the transaction count goes negative for a moment), but the phase cannot
@@ -196,6 +214,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
         }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      CE_TRACE(0, 2);
     }
     if constexpr (CG == 2) {
       // drain: every multicast commit aimed at this CTA's empty barriers must have landed before the
@@ -221,16 +240,20 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     int acc_stage = 0; uint32_t acc_phase = 0;
     TileWalk tw;
     tw.init(worker, num_m_units, num_tiles, num_workers);
-    for (; tw.item < num_items; tw.next()) {
+    for (int seq = 0; tw.item < num_items; tw.next(), ++seq) {
       const int ksp = tw.ksp;
       const int kb0 = ksp * gs.kblk_per_split;
       const int kb1 = min(kb0 + gs.kblk_per_split, gs.kblk_total);
+      CE_TRACE(1, 0);
       mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
       tc_fence_after();
+      CE_TRACE(1, 1);
       const uint32_t tmem_d = tmem_base + acc_stage * BN;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (kb == kb0) CE_TRACE(1, 2);
+        if (kb == kb1 - 1) CE_TRACE(1, 3);
         const uint32_t st = smem_u32(stage_base + (size_t)stage * Cfg::kStageBytes);
         const uint32_t sa_hi = st, sa_lo = st + Cfg::kABytes;
         const uint32_t sb_hi = st + Cfg::kParts * Cfg::kABytes, sb_lo = sb_hi + Cfg::kBBytes;
@@ -259,6 +282,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       // accumulator ready for the epilogue
       if constexpr (CG == 2) umma_commit_pair(&tfull_bar[acc_stage], 3);
       else umma_commit(&tfull_bar[acc_stage]);
+      CE_TRACE(1, 4);
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -284,13 +308,17 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       const int m_blk = tw.mu * CG + (int)cta_rank;
       epi.prefetch(tw.nb, et2, m_blk * kBM + et, m_blk * kBM + et < gs.M);
     }
-    for (; tw.item < num_items; tw = nx) {
+    for (int seq = 0; tw.item < num_items; tw = nx, ++seq) {
       const int ksp = tw.ksp;
+      const int trole = 2 + half;   // warps 4 and 8 (lane 0) trace the two column halves of quadrant 0
+#define CE_TRACE_E(k) do { if (q == 0 && lane == 0) CE_TRACE(trole, k); } while (0)
+      CE_TRACE_E(0);
       const int m_blk = tw.mu * CG + (int)cta_rank, n_blk = tw.nb;
       const bool tile_ok = CG == 1 || m_blk < gs.num_m_blk;   // odd row-block count: the peer idles
-      float* se = s_epi + acc_stage * (2 * BN);
+      float* se = s_epi + acc_stage * BN;
       epi.tile_begin(se, et2);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      CE_TRACE_E(1);
       const int row = m_blk * kBM + et;
       const bool row_ok = row < gs.M;
       epi.row_begin(row, row_ok);
@@ -299,8 +327,10 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
         const int nm = nx.mu * CG + (int)cta_rank;
         epi.prefetch(nx.nb, et2, nm * kBM + et, nm * kBM + et < gs.M);
       }
+      CE_TRACE_E(2);
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tc_fence_after();
+      CE_TRACE_E(3);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_stage * BN;
       if (tile_ok) {
 #pragma unroll 1
@@ -313,11 +343,13 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       }
       tc_fence_before();
       __syncwarp();
+      CE_TRACE_E(4);
       if (lane == 0) {
         if constexpr (CG == 2) mbar_arrive_cluster(map_to_cta(&tempty_bar[acc_stage], 0));
         else mbar_arrive(&tempty_bar[acc_stage]);
       }
       if (tile_ok) epi.row_end(row, row_ok, m_blk, n_blk, ksp, se, et, half);
+      CE_TRACE_E(5);
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
     epi.finish();
@@ -336,10 +368,11 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-// 2-D tensor map over a row-major [outer, inner] matrix with a 128-byte-wide box.
+// 2-D tensor map over a row-major [outer, inner] matrix.  swizzle: 0 = 128-byte (128-byte-wide
+// box), 1 = 128-byte with 32-byte atoms (tf32 MN-major operands), 2 = 64-byte (64-byte-wide box).
 int make_tmap(CUtensorMap* out, const void* ptr, bool fp32, uint64_t inner, uint64_t outer,
               uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer,
-              bool atom32 = false);
+              int swizzle = 0);
 
 struct GemmOperand {
   const void* ptr[2];  // hi, lo (lo null for bf16)
@@ -361,11 +394,21 @@ int build_tmaps(TmapSet* tm, GemmShape* gs, const GemmOperand& A, const GemmOper
   gs->kblk_per_split = (gs->kblk_total + k_splits - 1) / k_splits;
   gs->k_splits = (gs->kblk_total + gs->kblk_per_split - 1) / gs->kblk_per_split;
   gs->a_mn = A.mn_major; gs->b_mn = B.mn_major;
+  gs->trace = nullptr;
+#ifdef CE_GEMM_TRACE
+  {  // trace the CE_GEMM_TRACE_LAUNCH-th GEMM launch of this process into the buffer at CE_GEMM_TRACE_PTR
+    static int launch_no = 0;
+    const char* e = getenv("CE_GEMM_TRACE_PTR");
+    const char* n = getenv("CE_GEMM_TRACE_LAUNCH");
+    if (e != nullptr && ++launch_no == (n != nullptr ? atoi(n) : 1))
+      gs->trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+  }
+#endif
   for (int part = 0; part < Cfg::kParts; ++part) {
     if (!A.mn_major) CE_TRY(make_tmap(&tm->a[part], A.ptr[part], TF32X3, K, A.rows, A.ld, Cfg::kBK, kBM));
-    else CE_TRY(make_tmap(&tm->a[part], A.ptr[part], TF32X3, A.rows, K, A.ld, Cfg::kBK, Cfg::kBK, TF32X3));
+    else CE_TRY(make_tmap(&tm->a[part], A.ptr[part], TF32X3, A.rows, K, A.ld, Cfg::kBK, Cfg::kBK, TF32X3 ? 1 : 0));
     if (!B.mn_major) CE_TRY(make_tmap(&tm->b[part], B.ptr[part], TF32X3, K, B.rows, B.ld, Cfg::kBK, Cfg::kBRows));
-    else CE_TRY(make_tmap(&tm->b[part], B.ptr[part], TF32X3, B.rows, K, B.ld, Cfg::kBK, Cfg::kBK, TF32X3));
+    else CE_TRY(make_tmap(&tm->b[part], B.ptr[part], TF32X3, B.rows, K, B.ld, Cfg::kBK, Cfg::kBK, TF32X3 ? 1 : 0));
   }
   if (Cfg::kParts == 1) { tm->a[1] = tm->a[0]; tm->b[1] = tm->b[0]; }
   return CE_OK;
