@@ -35,6 +35,7 @@ struct GemmShape {
   int kblk_total;          // reduction length in BLOCK_K units
   int kblk_per_split;
   int a_mn, b_mn;          // operand majorness: 0 = K-major, 1 = MN-major
+  int raster_n;            // tile order: 0 = row units fastest, 1 = column blocks fastest
   long long* trace;        // -DCE_GEMM_TRACE builds only: per-tile clock64 stamps of CTA 0
 };
 
@@ -87,23 +88,29 @@ struct TmapSet {
 };
 
 // Walks the work items of one worker (item, item + W, ...) without a division per tile:
-// item = ksp * num_tiles + tile, tile = nb * nmu + mu.
+// item = ksp * num_tiles + tile, tile = outer * n_inner + inner.  The inner (fastest) tile index is
+// the row unit by default -- concurrent CTAs then share B tiles through L2 -- or the column block
+// (`raster_n`) when there are only a few column blocks and the A operand is the big one.
 struct TileWalk {
-  int nmu, num_tiles, W, w_mu, w_nb;
-  int item, tile, ksp, mu, nb;
-  __device__ __forceinline__ void init(int item0, int nmu_, int num_tiles_, int W_) {
-    nmu = nmu_; num_tiles = num_tiles_; W = W_;
-    w_nb = W / nmu; w_mu = W - w_nb * nmu;
+  int n_inner, num_tiles, W, w_in, w_out, raster_n;
+  int item, tile, ksp, in, out, mu, nb;
+  __device__ __forceinline__ void assign() { mu = raster_n ? out : in; nb = raster_n ? in : out; }
+  __device__ __forceinline__ void init(int item0, int nmu, int nnb, int W_, int raster_n_) {
+    raster_n = raster_n_;
+    n_inner = raster_n ? nnb : nmu; num_tiles = nmu * nnb; W = W_;
+    w_out = W / n_inner; w_in = W - w_out * n_inner;
     item = item0; ksp = item0 / num_tiles; tile = item0 - ksp * num_tiles;
-    nb = tile / nmu; mu = tile - nb * nmu;
+    out = tile / n_inner; in = tile - out * n_inner;
+    assign();
   }
   __device__ __forceinline__ void next() {
-    item += W; tile += W; mu += w_mu; nb += w_nb;
-    if (mu >= nmu) { mu -= nmu; ++nb; }
+    item += W; tile += W; in += w_in; out += w_out;
+    if (in >= n_inner) { in -= n_inner; ++out; }
     if (tile >= num_tiles) {   // next K split: rare, re-derive
       do { tile -= num_tiles; ++ksp; } while (tile >= num_tiles);
-      nb = tile / nmu; mu = tile - nb * nmu;
+      out = tile / n_inner; in = tile - out * n_inner;
     }
+    assign();
   }
 };
 
@@ -174,7 +181,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       else tma_load_2d(dst, m, &full_bar[st_idx], c0, c1);
     };
     TileWalk tw;
-    tw.init(worker, num_m_units, num_tiles, num_workers);
+    tw.init(worker, num_m_units, gs.num_n_blk, num_workers, gs.raster_n);
     for (int seq = 0; tw.item < num_items; tw.next(), ++seq) {
       const int ksp = tw.ksp;
       const int m_blk = tw.mu * CG + (int)cta_rank, n_blk = tw.nb;
@@ -239,7 +246,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     int stage = 0; uint32_t phase = 0;
     int acc_stage = 0; uint32_t acc_phase = 0;
     TileWalk tw;
-    tw.init(worker, num_m_units, num_tiles, num_workers);
+    tw.init(worker, num_m_units, gs.num_n_blk, num_workers, gs.raster_n);
     for (int seq = 0; tw.item < num_items; tw.next(), ++seq) {
       const int ksp = tw.ksp;
       const int kb0 = ksp * gs.kblk_per_split;
@@ -302,7 +309,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
     epi.out_map = &tm.out;
     epi.init();
     TileWalk tw, nx;
-    tw.init(worker, num_m_units, num_tiles, num_workers);
+    tw.init(worker, num_m_units, gs.num_n_blk, num_workers, gs.raster_n);
     nx = tw;
     if (worker < num_items) {
       const int m_blk = tw.mu * CG + (int)cta_rank;
@@ -394,6 +401,9 @@ int build_tmaps(TmapSet* tm, GemmShape* gs, const GemmOperand& A, const GemmOper
   gs->kblk_per_split = (gs->kblk_total + k_splits - 1) / k_splits;
   gs->k_splits = (gs->kblk_total + gs->kblk_per_split - 1) / gs->kblk_per_split;
   gs->a_mn = A.mn_major; gs->b_mn = B.mn_major;
+  // few column blocks over a tall A: run the column blocks of one row unit side by side, so that A
+  // is fetched from HBM once (measured on G^t x img at c3: 616 MB of DRAM reads for a 302 MB G)
+  gs->raster_n = (gs->num_n_blk > 1 && gs->num_n_blk * 8 <= gs->num_m_blk) ? 1 : 0;
   gs->trace = nullptr;
 #ifdef CE_GEMM_TRACE
   {  // trace the CE_GEMM_TRACE_LAUNCH-th GEMM launch of this process into the buffer at CE_GEMM_TRACE_PTR
