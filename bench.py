@@ -210,7 +210,7 @@ def main():
 
     ot_stream = torch.cuda.Stream()
 
-    def step():
+    def step(static=static, leaves=leaves, losses_out=losses_out):
         """fwd + bwd of the loss head as engine.py:48-67,88 drives it.  The two criteria are
         independent until the final sum, so the OT criterion is issued on a second stream: its
         ALU/HBM-bound kernels overlap the tensor-core GEMMs and the NCCL latencies (autograd runs
@@ -307,26 +307,68 @@ def main():
     value = w.B / (ms_step * 1e-3)
 
     # ---- e2e: host buffers -> public API -> host losses -------------------------------------
-    def e2e_step():
-        with torch.no_grad():
-            for k in ("img", "txt", "etxt", "obj", "tnum", "onum"):
-                static[k].copy_(host[k], non_blocking=True)
-        run()
-        losses_host.copy_(losses_out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    # Every step copies ITS inputs from pinned host memory and returns its three losses to the host.
+    # The loop is the one a training loop with a prefetching loader runs: two device input sets, the
+    # copy of step i+1 (copy stream) overlapping the kernels of step i; the timed region is the wall
+    # clock from the first copy to the last loss landing on the host.
+    sets = [(static, leaves, losses_out, run)]
+    if graph is not None:
+        try:
+            # the second set's warm-up runs on a side stream after the first set's graph exists
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            static_b = {k: v.detach().clone() for k, v in static.items()}
+            leaves_b = {k: static_b[k].requires_grad_(True) for k in ("img", "txt", "etxt", "obj")}
+            losses_b = torch.zeros(3, dtype=torch.float32, device=dev)
+            step_b = lambda: step(static_b, leaves_b, losses_b)   # noqa: E731
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_b()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_b, capture_error_mode="thread_local"):
+                step_b()
+            torch.cuda.synchronize()
+            sets.append((static_b, leaves_b, losses_b, graph_b.replay))
+        except Exception as e:  # pragma: no cover
+            torch.cuda.synchronize()
+            if rank == 0:
+                print("note: second input set not captured (%s); e2e runs unpipelined" % str(e)[:200], file=sys.stderr)
+    n_e2e = 3 + min(args.steps, 10)
+    losses_e2e = torch.zeros(n_e2e, 3, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
+    copied = [torch.cuda.Event() for _ in sets]
+    consumed = [torch.cuda.Event() for _ in sets]
 
-    t_e2e = []
-    for i in range(3 + min(args.steps, 10)):
-        barrier()
-        t0 = time.perf_counter()
-        e2e_step()
-        t_e2e.append(time.perf_counter() - t0)
-    e2e_s = torch.tensor([statistics.mean(t_e2e[3:])], device=dev)
+    def e2e_loop(first, last):
+        for i in range(first, last):
+            st_i, _, lo_i, run_i = sets[i % len(sets)]
+            with torch.cuda.stream(copy_stream), torch.no_grad():
+                copy_stream.wait_event(consumed[i % len(sets)])      # the step that last read this set
+                for k in ("img", "txt", "etxt", "obj", "tnum", "onum"):
+                    st_i[k].copy_(host[k], non_blocking=True)
+                copied[i % len(sets)].record(copy_stream)
+            main_stream.wait_event(copied[i % len(sets)])
+            run_i()
+            losses_e2e[i].copy_(lo_i, non_blocking=True)
+            consumed[i % len(sets)].record(main_stream)
+        main_stream.synchronize()
+
+    for ev in consumed:
+        ev.record(main_stream)
+    e2e_loop(0, 3)                                   # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(3, n_e2e)
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / (n_e2e - 3)], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    losses_host.copy_(losses_e2e[n_e2e - 1])
     h2d = sum(host[k].numel() * host[k].element_size() for k in host)
     e2e = {"value": w.B / float(e2e_s.item()), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": 12, "ms_per_step": float(e2e_s.item()) * 1e3}
+           "d2h_bytes_per_step": 12, "ms_per_step": float(e2e_s.item()) * 1e3,
+           "input_sets": len(sets), "steps": n_e2e - 3}
 
     # ---- per-chain timing for the rooflines (eager, events around each C-ABI chain) -----------
     def chain_contrastive():
