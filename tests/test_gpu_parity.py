@@ -386,3 +386,63 @@ def test_criterion_mode_errors():
         ce.CriterionContrastive("kl")(a, b, index_pos=idx)
     with pytest.raises(RuntimeError, match="does not match"):
         ce.CriterionContrastive("ce")(a, b, index_pos=idx, constrastive_overbatch=False)
+
+
+# ------------------------------------------------------------------------------------------
+# the tcgen05 GEMM engine by itself, and the loss head at the benchmark's size
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("entry", ["ce_debug_gemm", "ce_debug_gemm_pair"])
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,split_k", [
+    (256, 256, 64, 0, 0, 1), (100, 200, 72, 0, 0, 1), (1024, 2304, 512, 0, 0, 1), (256, 256, 2048, 0, 0, 4),
+    (256, 256, 64, 1, 0, 1), (256, 256, 64, 0, 1, 1), (520, 512, 1000, 0, 1, 1), (2304, 512, 1024, 1, 1, 3),
+    (4608, 512, 640, 1, 1, 1),      # tall A, two column blocks: column-fastest tile order
+    (384, 256, 128, 0, 0, 1),       # odd number of 128-row blocks: the pair's second CTA idles on the last unit
+])
+def test_tcgen05_gemm_engine_bit_exact(entry, M, N, K, a_mn, b_mn, split_k):
+    """C = A B^t through the TMA + tcgen05 main loop (single-CTA and CTA-pair flavours), K-major
+    and MN-major operands, split-K: small-integer inputs make every product and sum exact."""
+    from clip_event_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randint(-3, 4, (M, K), generator=g).float()
+    B = torch.randint(-3, 4, (N, K), generator=g).float()
+    Ad = (A.t().contiguous() if a_mn else A).bfloat16().cuda()
+    Bd = (B.t().contiguous() if b_mn else B).bfloat16().cuda()
+    C = torch.full((M, N), float("nan"), device="cuda")
+    rc = getattr(lib, entry)(Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), M, N, K, L.dtype_code(torch.bfloat16),
+                             a_mn, b_mn, split_k, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, L.last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(C.cpu(), A @ B.t())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_benchmark_size_vs_torch_fp32(dtype):
+    """The bench workload (c3: 4096 images x 36864 descriptions, D = 512) against the same maths in
+    plain PyTorch fp32 on the GPU -- the only test large enough to reach the CTA-pair GEMMs, the
+    column-fastest tile order and several waves of the persistent kernels."""
+    w = syn.WORKLOADS["c3"]
+    img, txt, ls = syn.contrastive_inputs(w.B, w.T, w.D, 3, "trained", dtype=dtype)
+    lpi, lpt, idx = syn.contrastive_labels(w.B, w.T)
+    li, lt, dimg, dtxt, dls = run_contrastive(img, txt, ls, lpi, lpt, idx)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        i32 = img.float().cuda().requires_grad_(True)
+        t32 = txt.float().cuda().requires_grad_(True)
+        l32 = ls.float().cuda().requires_grad_(True)
+        logits = l32.exp() * (i32 / i32.norm(dim=1, keepdim=True)) @ (t32 / t32.norm(dim=1, keepdim=True)).t()
+        ref_i = torch.nn.functional.cross_entropy(logits, lpi.cuda())
+        ref_t = torch.nn.functional.cross_entropy(logits.t()[idx.cuda()], lpt.cuda()[idx.cuda()])
+        (ref_i + ref_t).backward()
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    if dtype == torch.float32:
+        lr, la, gt = 2e-5, 4e-6, 5e-5        # the fp32 reference itself carries ~1e-6 at this size
+    else:
+        lr, la, gt = BF16_LOSS_RTOL, 0.0, BF16_GRAD
+    assert close(li, ref_i.item(), lr, la) and close(lt, ref_t.item(), lr, la)
+    assert rel_err(dimg, i32.grad.cpu()) < gt
+    assert rel_err(dtxt, t32.grad.cpu()) < gt
+    assert close(dls, l32.grad.item(), 1e-2 if dtype != torch.float32 else 2e-4, 1e-4)
