@@ -8,8 +8,9 @@ One JSON line on rank 0 (see DESIGN.md "Measurement" for every field).  A step i
 backward of the whole loss head over one synthetic batch:
   * ``value``     samples/s with the inputs already resident in HBM (CUDA-graph replay of the public
                   API's fwd+bwd, timed with CUDA events, max over ranks);
-  * ``e2e``       the same through the reference-facing modules with HOST (pinned) inputs: per step
-                  H2D of every input, fwd+bwd, D2H of the losses, host sync;
+  * ``e2e``       the same through the reference-facing modules with HOST (pinned) inputs: every
+                  step copies its inputs H2D and returns its losses D2H; two device input sets, so
+                  the copy of step i+1 overlaps the kernels of step i (wall clock over the loop);
   * ``roofline``  for the dominant kernel chain, from CUDA-event timings taken in this run;
   * ``cpu_baseline`` the oracle (reference algorithm, PyTorch CPU) on a bounded sample, rank 0, N=1.
 Multi-GPU (torchrun): strong scaling -- the GLOBAL batch of the workload is sharded over the ranks;
@@ -422,6 +423,15 @@ def main():
                "achieved": ot_bytes / (ms_ot * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                "frac": ot_bytes / (ms_ot * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "ms": ms_ot,
                "peak_source": peaks["source"] + " copy bandwidth"}
+    # DRAM traffic per step of each chain, from the committed ncu --set full captures of the same
+    # workload (profiles/r01_traffic_*.json; null when there is no capture for this configuration)
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_%s_%s.json" % (w.name, args.dtype))
+    if world == 1 and os.path.exists(tpath):
+        with open(tpath) as f:
+            tr = json.load(f)
+        roof_gemm["traffic"] = tr.get("gemm_chain_bytes_per_step")
+        roof_ot["traffic"] = tr.get("ot_chain_bytes_per_step")
+        roof_gemm["traffic_source"] = roof_ot["traffic_source"] = "profiles/" + os.path.basename(tpath)
     dominant, secondary = (roof_gemm, roof_ot) if ms_con >= ms_ot else (roof_ot, roof_gemm)
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
