@@ -446,3 +446,36 @@ def test_benchmark_size_vs_torch_fp32(dtype):
     assert rel_err(dimg, i32.grad.cpu()) < gt
     assert rel_err(dtxt, t32.grad.cpu()) < gt
     assert close(dls, l32.grad.item(), 1e-2 if dtype != torch.float32 else 2e-4, 1e-4)
+
+
+def test_integration_md_ctypes_stubs_run():
+    """The two ctypes stubs printed in INTEGRATION.md (route B) are executed verbatim against the
+    built library and must agree with the shipped Python mirror."""
+    import os
+    import re
+    from clip_event_b200 import _lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    ns = {}
+    for blk in blocks:
+        if "def ot_loss_and_grads" in blk or "def contrastive_losses_and_grads" in blk:
+            exec(blk.replace('"libclip_event_b200.so"', repr(L.LIB_PATH)), ns)
+    assert "ot_loss_and_grads" in ns and "contrastive_losses_and_grads" in ns
+    w = syn.WORKLOADS["c2"]
+    for dtype in (torch.float32, torch.bfloat16):
+        img, txt, ls = syn.contrastive_inputs(w.B, w.T, w.D, 5, "trained", dtype=dtype)
+        lpi, lpt, idx = syn.contrastive_labels(w.B, w.T)
+        li, lt, dimg, dtxt, dls = run_contrastive(img, txt, ls, lpi, lpt, idx)
+        a, b, gi, gt, gl = ns["contrastive_losses_and_grads"](img.cuda(), txt.cuda(), ls.float().reshape(1).cuda(),
+                                                             lpi.cuda(), lpt.cuda(), idx.cuda())
+        torch.cuda.synchronize()
+        assert a.item() == li and b.item() == lt
+        # split-K partial sums meet in red.add, so gradients repeat to rounding, not bit for bit
+        assert rel_err(gi, dimg) < 1e-5 and rel_err(gt, dtxt) < 1e-5 and close(gl.item(), dls, 1e-5, 1e-7)
+        etxt, obj, tnum, onum = syn.ot_inputs(32, w.M, w.N, w.D, 6, "ragged", dtype=dtype)
+        loss, dist, dt_, do_ = run_ot(etxt, obj, tnum, onum)
+        l2, d2, dt2, do2 = ns["ot_loss_and_grads"](etxt.cuda(), obj.cuda(), tnum.cuda(), onum.cuda())
+        torch.cuda.synchronize()
+        assert l2.item() == loss and torch.equal(d2.cpu(), dist)
+        assert torch.equal(dt2.cpu(), dt_) and torch.equal(do2.cpu()[:, 1:], do_[:, 1:])
