@@ -141,10 +141,14 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
   // [8 warps][kStageBytesPerWarp], 1024-byte aligned (swizzled TMA-store source)
   uint8_t* epi_stage = smem + Cfg::kEpiStageOffset;
 
-  const int warp = warp_id(), lane = lane_id();
+  // The control warps run their loops with all 32 lanes converged and let one elected lane issue
+  // the TMA / tcgen05 instructions: the operands are then provably warp-uniform and live in uniform
+  // registers (issuing from a `lane == 0` branch costs an R2UR + election loop per instruction,
+  // and the MMA issue path was as long as the MMAs themselves).
+  const int warp = __shfl_sync(0xffffffffu, warp_id(), 0), lane = lane_id();
   // CG == 2: CTAs 2w and 2w+1 form worker w; CTA rank r owns rows [(2*unit + r) * 128, +128) of the
   // 256-row unit and stages columns [r * BN/2, +BN/2) of the B tile.  Rank 0 (the leader) issues the MMAs.
-  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = CG == 2 ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;
   const int worker = (int)blockIdx.x / CG, num_workers = (int)gridDim.x / CG;
   const int num_m_units = (gs.num_m_blk + CG - 1) / CG;
   const int num_tiles = num_m_units * gs.num_n_blk;
@@ -172,7 +176,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ================= TMA producer =================
     int stage = 0; uint32_t phase = 0;
     // pair mode: completion is signalled on the LEADER's full barrier (a shared::cluster address)
@@ -192,6 +196,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (kb == kb0) CE_TRACE(0, 1);
+        if (elect_one()) {
         uint8_t* st = stage_base + (size_t)stage * Cfg::kStageBytes;
         // The peer never arrives on the leader's barrier: its bytes may land before the leader's
         // expect_tx (the transaction count goes negative for a moment), but the phase cannot
@@ -219,6 +224,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
                    kb * Cfg::kBK);
           }
         }
+        }
+        __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
       CE_TRACE(0, 2);
@@ -231,7 +238,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+  } else if (warp == 1 && cta_rank == 0) {
     // ================= MMA issuer (pair mode: the leader CTA only) =================
     const uint32_t idesc = umma_idesc(TF32X3, kBM * CG, BN, gs.a_mn != 0, gs.b_mn != 0);
     // K-major: 8-row groups 1024 B apart, K advances 32 B inside the swizzle atom.
@@ -261,6 +268,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
         tc_fence_after();
         if (kb == kb0) CE_TRACE(1, 2);
         if (kb == kb1 - 1) CE_TRACE(1, 3);
+        if (elect_one()) {
         const uint32_t st = smem_u32(stage_base + (size_t)stage * Cfg::kStageBytes);
         const uint32_t sa_hi = st, sa_lo = st + Cfg::kABytes;
         const uint32_t sb_hi = st + Cfg::kParts * Cfg::kABytes, sb_lo = sb_hi + Cfg::kBBytes;
@@ -284,11 +292,16 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
         // frees the smem stage (in both CTAs of a pair) once these MMAs retire
         if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 3);
         else umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
       // accumulator ready for the epilogue
-      if constexpr (CG == 2) umma_commit_pair(&tfull_bar[acc_stage], 3);
-      else umma_commit(&tfull_bar[acc_stage]);
+      if (elect_one()) {
+        if constexpr (CG == 2) umma_commit_pair(&tfull_bar[acc_stage], 3);
+        else umma_commit(&tfull_bar[acc_stage]);
+      }
+      __syncwarp();
       CE_TRACE(1, 4);
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
