@@ -27,7 +27,7 @@ def _nvcc() -> str:
 
 
 def _stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or os.environ.get("CE_EXTRA_NVCC_FLAGS"):
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
@@ -37,13 +37,15 @@ def _stale() -> bool:
 def _compile(src: str) -> str:
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
     deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    if os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
-        return obj
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
     flags += os.environ.get("CE_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DCE_GEMM_TRACE (tools/gemm_trace.py)
     cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
-    r = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(OBJ, src.replace(".cu", ".log"))
+    if os.path.exists(obj) and os.path.exists(log) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
+        with open(log) as f:
+            if f.readline().rstrip("\n") == " ".join(cmd):   # same sources AND same command line
+                return obj
+    r = subprocess.run(cmd, capture_output=True, text=True)
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:

@@ -343,6 +343,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
       const bool row_ok = row < gs.M;
       epi.row_begin(row, row_ok);
       nx.next();
+      CE_TRACE_E(6);
       if (nx.item < num_items) {
         const int nm = nx.mu * CG + (int)cta_rank;
         epi.prefetch(nx.nb, et2, nm * kBM + et, nm * kBM + et < gs.M);

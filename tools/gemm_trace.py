@@ -32,7 +32,7 @@ a, b = F_.contrastive_over_batch(img, txt, ls, lpi, lpt, idx)
 torch.cuda.synchronize()
 t = buf.cpu().view(64, 4, 8)
 names = {0: ["tile", "empty0 ok", "issued"], 1: ["tile", "tempty ok", "full0 ok", "fullN ok", "commit"],
-         2: ["tile", "bar ok", "prefetched", "tfull ok", "chunks done", "row_end"], 3: None}
+         2: ["tile", "bar ok", "prefetched", "tfull ok", "chunks done", "row_end", "walked"], 3: None}
 names[3] = names[2]
 base = int(t[0, 1, 0])
 print("GEMM launch %s; cycles relative to the MMA thread's first tile" % os.environ["CE_GEMM_TRACE_LAUNCH"])
