@@ -17,4 +17,4 @@ timeout 600 ncu --set full --clock-control none --import-source on --kernel-name
 timeout 120 python tools/ot_tune.py c3 bf16 > gpurun_out/ot_tune_c3.log 2>&1 || exit 1
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:ot_" -s 30 -c 4 \
     -o gpurun_out/prof_r01_ot python tools/ot_tune.py c3 bf16 > gpurun_out/ncu_ot.log 2>&1
-tail -2 gpurun_out/con_tune_c3.log gpurun_out/ot_tune_c3.log
+tail -n 2 gpurun_out/con_tune_c3.log; tail -n 2 gpurun_out/ot_tune_c3.log
