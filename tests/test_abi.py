@@ -46,6 +46,8 @@ def test_built_for_sm100a_with_tcgen05_and_tma():
     assert "UTCHMMA" in sass, "tcgen05.mma missing from SASS"
     assert "UTMALDG" in sass, "TMA loads missing from SASS"
     assert "LDTM" in sass, "tcgen05.ld missing from SASS"
+    assert "UTCHMMA.2CTA" in sass, "tcgen05.mma.cta_group::2 (CTA-pair GEMM) missing from SASS"
+    assert "UTMASTG" in sass, "TMA stores (gradient-tile epilogue) missing from SASS"
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
