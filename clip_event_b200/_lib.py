@@ -10,7 +10,7 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libclip_event_b200.so")
+LIB_PATH = os.environ.get("CE_LIB_PATH") or os.path.join(_PKG, "libclip_event_b200.so")
 
 CE_F32, CE_BF16 = 0, 1
 CE_MASK_NUM_I64, CE_MASK_PAD_U8 = 0, 1
