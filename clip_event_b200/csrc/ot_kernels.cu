@@ -1279,16 +1279,11 @@ int launch_ipot_mp(const IpotArgs& a, int N, cudaStream_t st, bool* handled) {
   const int rptw = (N + 32 / TC - 1) / (32 / TC);
   const int rpt256 = (N + 256 / TC - 1) / (256 / TC);
   const int rpt512 = (N + 512 / TC - 1) / (512 / TC);
-  static const int variant = getenv("CE_IPOT_VARIANT") ? atoi(getenv("CE_IPOT_VARIANT")) : 0;  // tuning aid
 #define CE_IPOT_CASE(COND, R, G, ...) \
   if (COND <= R) { ot_ipot_kernel<MP, R, G, ##__VA_ARGS__><<<(G == 32 ? (a.B + 7) / 8 : a.B), (G < 256 ? 256 : G), 0, st>>>(a); return CE_OK; }
   CE_IPOT_CASE(rptw, 2, 32, 2) CE_IPOT_CASE(rptw, 4, 32, 2) CE_IPOT_CASE(rptw, 7, 32, 2) CE_IPOT_CASE(rptw, 10, 32)
   CE_IPOT_CASE(rpt256, 1, 256) CE_IPOT_CASE(rpt256, 2, 256) CE_IPOT_CASE(rpt256, 4, 256)
-  if (MP == 32 && variant == 1) { CE_IPOT_CASE(rpt256, 9, 256, 1, 0) }
-  if (MP == 32 && variant == 2) { CE_IPOT_CASE(rpt512, 5, 512, 1, 0) }
-  if (MP == 32 && variant == 3) { CE_IPOT_CASE(rpt256, 9, 256, 2, 1) }
-  if (MP == 32 && variant == 4) { CE_IPOT_CASE(rpt256, 9, 256, 1, 1) }
-  if (MP == 32 && variant == 5) { CE_IPOT_CASE(rpt512, 5, 512, 1, 1) }
+  // (measured at c4 and dropped: 512 threads per sample, and the two-barrier SCHEME 1 at either size)
   CE_IPOT_CASE(rpt256, 7, 256, 2, 0) CE_IPOT_CASE(rpt256, 9, 256, 2, 0) CE_IPOT_CASE(rpt256, 13, 256)
   CE_IPOT_CASE(rpt512, 10, 512) CE_IPOT_CASE(rpt512, 13, 512)
   if (rpt512 <= 20) {   // kernel matrix in shared memory (64 x 577 and the like)

@@ -1,5 +1,5 @@
-"""Times ce_ot_fwd_bwd (forward only = cost + IPOT, and full) for a workload; run once per
-CE_IPOT_VARIANT in a fresh process:  CE_IPOT_VARIANT=3 python tools/ot_tune.py c4 bf16"""
+"""Times ce_ot_fwd_bwd (forward only = cost + IPOT, and full) for a workload:
+python tools/ot_tune.py c4 bf16 [batch]"""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -32,5 +32,5 @@ def time_it(fn, n=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 l, d = fwd()
-print("variant=%s %s %s B=%d: fwd(cost+ipot) %.1f us   full %.1f us   loss %.6f" % (
-    os.environ.get("CE_IPOT_VARIANT", "0"), wl, sys.argv[2], B, time_it(fwd), time_it(full), l.item()))
+print("%s %s B=%d: fwd(cost+ipot) %.1f us   full %.1f us   loss %.6f" % (
+    wl, sys.argv[2], B, time_it(fwd), time_it(full), l.item()))
