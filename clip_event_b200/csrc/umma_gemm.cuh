@@ -1,20 +1,22 @@
 // Persistent, warp-specialised tcgen05 GEMM engine for sm_100a.
 //
 //   acc[128 x BN] (fp32, TMEM) = A_tile * B_tile^t   over a K range, A/B tiles staged by TMA into
-//   128-byte-swizzled shared memory, `tcgen05.mma` issued by one thread, accumulators double
+//   128-byte-swizzled shared memory, `tcgen05.mma` issued by one elected lane, accumulators double
 //   buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4..11 = epilogue: warp w reads TMEM lanes 32*(w%4).. and the column half
-// (w-4)/4 of the tile, so two warps share each row.
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (both run their loops with
+// all lanes converged, one elected lane issues), warp 2 = TMEM allocator, warps 4..11 = epilogue:
+// warp w reads TMEM lanes 32*(w%4).. and the column half (w-4)/4 of the tile, so two warps share
+// each row.  CG = 2 runs the same roles on a CTA pair: one 256 x BN tile per pair, the leader CTA
+// issues `tcgen05.mma.cta_group::2` for both, each CTA stages half of the B tile.
 //
 // Operand precision: bf16 (kind::f16, one product) or fp32 carried as a (hi, lo) pair of tf32
 // arrays with three products hi*hi + hi*lo + lo*hi (kind::tf32) -- fp32-level accuracy.
 // Operand layouts: K-major ([rows, K] row-major) or MN-major ([K, rows] row-major), both through
 // the canonical SWIZZLE_128B shared-memory layouts.
 //
-// The epilogue is a functor template parameter: row/column softmax statistics, on-the-fly softmax
-// gradient, or plain scaled store / split-K accumulate.
+// The epilogue is a functor template parameter: row softmax statistics, on-the-fly softmax
+// gradient (TMA-stored), or plain scaled store / split-K accumulate.
 #pragma once
 
 #include <stdlib.h>
@@ -114,12 +116,18 @@ struct TileWalk {
   }
 };
 
-// Epilogue interface:
-//   struct Epi { Params p;
-//     __device__ void tile_begin(float* s_epi, int m_blk, int n_blk, int et /*0..127*/);   (all 128 epilogue threads, followed by a 128-thread barrier)
-//     __device__ void row_begin(int row /*global row*/, bool row_ok);
-//     __device__ void chunk(const float* acc /*32 cols*/, int col0 /*global col of acc[0]*/, int lcol0 /*tile-local*/, const float* s_epi);
-//     __device__ void row_end(int row, bool row_ok, int m_blk, int n_blk, int k_split, float* s_epi, int et);
+// Epilogue interface (one object per epilogue thread; `et2` = 0..255 among the epilogue threads,
+// `half` = which 128-column half of the tile this warp handles):
+//   struct Epi { struct Params {...}; Params p; uint8_t* stage; const CUtensorMap* out_map;
+//     static constexpr int kStageBytesPerWarp;     // shared-memory staging the kernel reserves per warp
+//     void init();                                  // once per kernel
+//     void prefetch(int n_blk, int et2, int row, bool row_ok);   // global loads for the NEXT tile
+//     void tile_begin(float* s_epi, int et2);       // publish column data; a 256-thread barrier follows
+//     void row_begin(int row, bool row_ok);
+//     void chunk(const float* acc /*32 columns of this thread's row*/, int col0 /*global column*/,
+//                int lcol0 /*tile-local column*/, const float* s_epi, int row, bool row_ok);
+//     void row_end(int row, bool row_ok, int m_blk, int n_blk, int k_split, float* s_epi, int et, int half);
+//     void finish();                                // once, after the last tile
 //   };
 
 template <bool TF32X3, int BN, class Epi, int CG = 1>
