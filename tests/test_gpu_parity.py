@@ -416,14 +416,15 @@ def test_tcgen05_gemm_engine_bit_exact(entry, M, N, K, a_mn, b_mn, split_k):
     assert torch.equal(C.cpu(), A @ B.t())
 
 
+@pytest.mark.parametrize("B,T,D", [(4096, 9, 512), (2000, 9, 520)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_benchmark_size_vs_torch_fp32(dtype):
+def test_benchmark_size_vs_torch_fp32(dtype, B, T, D):
     """The bench workload (c3: 4096 images x 36864 descriptions, D = 512) against the same maths in
     plain PyTorch fp32 on the GPU -- the only test large enough to reach the CTA-pair GEMMs, the
-    column-fastest tile order and several waves of the persistent kernels."""
-    w = syn.WORKLOADS["c3"]
-    img, txt, ls = syn.contrastive_inputs(w.B, w.T, w.D, 3, "trained", dtype=dtype)
-    lpi, lpt, idx = syn.contrastive_labels(w.B, w.T)
+    column-fastest tile order and several waves of the persistent kernels.  The second shape hits
+    the same paths with ragged edges in every dimension (rows, columns, a partial k-block)."""
+    img, txt, ls = syn.contrastive_inputs(B, T, D, 3, "trained", dtype=dtype)
+    lpi, lpt, idx = syn.contrastive_labels(B, T)
     li, lt, dimg, dtxt, dls = run_contrastive(img, txt, ls, lpi, lpt, idx)
     old = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
