@@ -240,11 +240,10 @@ def main():
             loss_dict = crit(a, b_, lpi, lpt, index_pos=idx, constrastive_overbatch=True)
         main.wait_stream(ot_stream)
         loss_dict["loss_ot"] = loss_ot
-        total = sum(v.float() for v in loss_dict.values())
+        total = sum(loss for loss in loss_dict.values())     # engine.py:67, in the losses' own dtype
         total.backward()
         main.wait_stream(ot_stream)
-        losses_out.copy_(torch.stack([loss_dict["loss_i"].float(), loss_dict["loss_t"].float(),
-                                      loss_dict["loss_ot"].float()]))
+        losses_out.copy_(torch.stack([loss_dict["loss_i"], loss_dict["loss_t"], loss_dict["loss_ot"]]))
 
     def barrier():
         if world > 1:
