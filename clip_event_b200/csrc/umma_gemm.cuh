@@ -96,8 +96,8 @@ struct TmapSet {
 struct TileWalk {
   int n_inner, num_tiles, W, w_in, w_out, raster_n;
   int item, tile, ksp, in, out, mu, nb;
-  __device__ __forceinline__ void assign() { mu = raster_n ? out : in; nb = raster_n ? in : out; }
-  __device__ __forceinline__ void init(int item0, int nmu, int nnb, int W_, int raster_n_) {
+  __host__ __device__ __forceinline__ void assign() { mu = raster_n ? out : in; nb = raster_n ? in : out; }
+  __host__ __device__ __forceinline__ void init(int item0, int nmu, int nnb, int W_, int raster_n_) {
     raster_n = raster_n_;
     n_inner = raster_n ? nnb : nmu; num_tiles = nmu * nnb; W = W_;
     w_out = W / n_inner; w_in = W - w_out * n_inner;
@@ -105,7 +105,7 @@ struct TileWalk {
     out = tile / n_inner; in = tile - out * n_inner;
     assign();
   }
-  __device__ __forceinline__ void next() {
+  __host__ __device__ __forceinline__ void next() {
     item += W; tile += W; in += w_in; out += w_out;
     if (in >= n_inner) { in -= n_inner; ++out; }
     if (tile >= num_tiles) {   // next K split: rare, re-derive
