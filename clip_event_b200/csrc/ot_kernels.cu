@@ -1094,12 +1094,13 @@ __global__ void ot_tail_kernel(const float* dist, int B, float scale, float* los
     s = warp_sum(s);
     if (threadIdx.x == 0) *loss = s * scale;
   }
-  if (slot0 != nullptr) {
-    int64_t total = (int64_t)B * D;
+  if (slot0 != nullptr) {   // rows are 16-byte aligned multiples of 16 bytes (checked by the caller)
+    const int ppr = D * (int)sizeof(T) / 16;          // 16-byte pieces per row
+    const int64_t total = (int64_t)B * ppr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
-      int b = (int)(i / D), d = (int)(i % D);
-      In<DT>::st(reinterpret_cast<T*>(slot0) + (int64_t)b * bs + d, 0.f);
+      const int b = (int)(i / ppr), pc = (int)(i - (int64_t)b * ppr);
+      reinterpret_cast<uint4*>(reinterpret_cast<T*>(slot0) + (int64_t)b * bs)[pc] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
 }
@@ -1391,7 +1392,7 @@ extern "C" int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* i
   }
   {
     void* slot = dtxt != nullptr ? dimg_slot0 : nullptr;
-    int blocks = slot ? (int)std::min<int64_t>(((int64_t)B * D + 255) / 256, 148 * 4) : 1;
+    int blocks = slot ? (int)std::min<int64_t>(((int64_t)B * D * (int64_t)esz / 16 + 255) / 256, 148 * 4) : 1;
     if (dtype == CE_F32) ot_tail_kernel<CE_F32><<<blocks, 256, 0, st>>>(dist, B, loss_scale, loss, slot, img_bstride, D);
     else ot_tail_kernel<CE_BF16><<<blocks, 256, 0, st>>>(dist, B, loss_scale, loss, slot, img_bstride, D);
     CE_LAUNCH_CHECK();

@@ -179,8 +179,17 @@ class _OtAlignment(torch.autograd.Function):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         dist = torch.empty(B, dtype=torch.float32, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
-        dtxt = torch.empty_like(txt_c) if need_grad else None
-        dobj = torch.empty_like(obj_c) if need_grad else None
+        # both gradients live in one allocation, so the backward is ONE scale launch over it
+        if need_grad:
+            n_t = txt_c.numel()
+            n_t_pad = (n_t + 7) // 8 * 8                     # keeps dobj 16-byte aligned
+            gbuf = torch.empty(n_t_pad + obj_c.numel(), dtype=txt_c.dtype, device=dev)
+            if n_t_pad != n_t:
+                gbuf[n_t:n_t_pad].zero_()
+            dtxt = gbuf[:n_t].view_as(txt_c)
+            dobj = gbuf[n_t_pad:].view_as(obj_c)
+        else:
+            gbuf = dtxt = dobj = None
         L.check(lib.ce_ot_fwd_bwd(
             txt_c.data_ptr(), M * D, obj_c.data_ptr() + slot * D * esz, (N + slot) * D,
             tm.data_ptr(), M, om.data_ptr() + slot * msz, N + slot, kind_t, B, M, N, D, dt,
@@ -188,7 +197,7 @@ class _OtAlignment(torch.autograd.Function):
             L.ptr(dtxt), 0 if dobj is None else dobj.data_ptr() + slot * D * esz,
             0 if (dobj is None or not slot) else dobj.data_ptr(), ws.data_ptr(), nbytes, L.stream_ptr()),
             "OT forward")
-        ctx.stash = (dtxt, dobj)
+        ctx.stash = (dtxt, dobj, gbuf)
         ctx.loss_scale = float(loss_scale)
         ctx.consumed = False
         ctx.set_materialize_grads(False)   # an unused output arrives as None, not as zeros
@@ -199,11 +208,11 @@ class _OtAlignment(torch.autograd.Function):
         if ctx.consumed:
             raise RuntimeError("clip_event_b200 OT: backward through the stashed gradients a second time; "
                                "run the forward again (retain_graph is not supported on this path)")
-        dtxt, dobj = ctx.stash
+        dtxt, dobj, gbuf = ctx.stash
         if dtxt is None:
             return (None,) * 9
         ctx.consumed = True
-        ctx.stash = (None, None)
+        ctx.stash = (None, None, None)
         dev = dtxt.device
         if g_dist is not None:
             # per-sample upstream gradients (optimal_transport_dist users): general path
@@ -215,9 +224,8 @@ class _OtAlignment(torch.autograd.Function):
         g = _scalar_f32(g_loss, dev)
         lib = L.load()
         dt = L.dtype_code(dtxt.dtype)
-        for t in (dtxt, dobj):
-            L.check(lib.ce_scale_inplace(t.data_ptr(), 1, t.numel(), t.numel(), dt, g.data_ptr(), L.stream_ptr()),
-                    "OT backward scale")
+        L.check(lib.ce_scale_inplace(gbuf.data_ptr(), 1, gbuf.numel(), gbuf.numel(), dt, g.data_ptr(), L.stream_ptr()),
+                "OT backward scale")
         return dtxt, dobj, None, None, None, None, None, None, None
 
 
