@@ -162,9 +162,11 @@ class _GlobalContrastive(torch.autograd.Function):
         img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset, state = ctx.saved
         group, compute, world, rank, b, ls_dtype, ls_shape = ctx.meta
         dev = txt_c.device
-        zero = torch.zeros(1, dtype=torch.float32, device=dev)
-        gi = zero if g_i is None else g_i.detach().to(torch.float32).reshape(1).contiguous()
-        gt = zero if g_t is None else g_t.detach().to(torch.float32).reshape(1).contiguous()
+        def scalar(g):   # a missing upstream gradient is a zero; no launch when both are present
+            if g is None:
+                return torch.zeros(1, dtype=torch.float32, device=dev)
+            return g.detach().to(torch.float32).reshape(1).contiguous()
+        gi, gt = scalar(g_i), scalar(g_t)
         R_total = img_all.shape[0]
         P_total = index_pos.numel() * world   # ranks hold equal shards
         dtxt, dimg_hat, dls = compute.bwd_partial(img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset,

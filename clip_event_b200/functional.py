@@ -79,9 +79,9 @@ class _ContrastiveOverBatch(torch.autograd.Function):
         img, txt, ls, labels_i, labels_t, index_pos, ws = ctx.saved_tensors
         B, BT, P, D, dt, mode = ctx.dims
         dev = img.device
-        zero = torch.zeros(1, dtype=torch.float32, device=dev)
-        gi = zero if g_i is None else _scalar_f32(g_i, dev)
-        gt = zero if g_t is None else _scalar_f32(g_t, dev)
+        # a missing upstream gradient is a zero; no fill launch when both are present
+        gi = torch.zeros(1, dtype=torch.float32, device=dev) if g_i is None else _scalar_f32(g_i, dev)
+        gt = torch.zeros(1, dtype=torch.float32, device=dev) if g_t is None else _scalar_f32(g_t, dev)
         dimg, dtxt = torch.empty_like(img), torch.empty_like(txt)
         dls = torch.empty(1, dtype=torch.float32, device=dev)
         lib = L.load()
