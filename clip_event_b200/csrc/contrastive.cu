@@ -426,9 +426,17 @@ struct PrepAllArgs {
   int64_t col_offset;
   float *rinv_i, *norm_i, *rinv_t, *norm_t, *rinv_p, *norm_p;
   void *img0, *img1, *txt0, *txt1, *pos0, *pos1;
-  int *lab_local, *lab_t, *col_pos;          // col_pos is pre-set to -1 by a memset
+  int *lab_local, *lab_t, *col_pos;          // col_pos: -1 here, the positives' slots are set by fwd_items_kernel
   float *lab_logit_i, *lab_logit_t;
+  int* status;                               // [0] input-error bits, [1] block ticket of fwd_items_kernel
+  int64_t label_hi;                          // labels_per_image must lie in [0, label_hi)
 };
+// Input errors (the reference raises an IndexError / device assert for them; here the indices are
+// clamped so that nothing is read or written out of bounds, and both losses come back as NaN):
+constexpr int kErrLabelImage = 1;   // labels_per_image outside [0, number of descriptions)
+constexpr int kErrIndexPos = 2;     // index_pos outside [0, C) or labels_per_text[index_pos] outside [0, R)
+constexpr int kErrDupPos = 4;       // index_pos lists a description twice
+constexpr int kLabBad = -2;
 template <int DT>
 __device__ __forceinline__ void prep_one_row(const void* src, int64_t sr, int r, int D, float* rinv,
                                              float* norm, void* out0, void* out1) {
@@ -469,25 +477,32 @@ __device__ __forceinline__ void prep_one_row(const void* src, int64_t sr, int r,
 template <int DT>
 __global__ void prep_all_kernel(PrepAllArgs a) {
   const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wi == 0 && lane == 0) { a.status[0] = 0; a.status[1] = 0; }   // consumed by later launches of this stream
   if (wi < a.R) {
     prep_one_row<DT>(a.img, wi, wi, a.D, a.rinv_i, a.norm_i, a.img0, a.img1);
     if (lane == 0) {
-      int64_t lab = a.labels_i != nullptr ? a.labels_i[wi] - a.col_offset : -1;
-      a.lab_local[wi] = (lab >= 0 && lab < a.C) ? (int)lab : -1;
+      int v = -1;
+      if (a.labels_i != nullptr) {
+        const int64_t lg = a.labels_i[wi], lab = lg - a.col_offset;
+        v = (lg < 0 || lg >= a.label_hi) ? kLabBad : ((lab >= 0 && lab < a.C) ? (int)lab : -1);
+      }
+      a.lab_local[wi] = v;
       a.lab_logit_i[wi] = 0.f;
     }
   } else if (wi < a.R + a.C) {
     const int c = wi - a.R;
     prep_one_row<DT>(a.txt, c, c, a.D, a.rinv_t, a.norm_t, a.txt0, a.txt1);
+    if (lane == 0) a.col_pos[c] = -1;
   } else if (wi < a.R + a.C + a.P) {
     const int p = wi - a.R - a.C;
-    const int64_t col = a.index_pos[p];
+    int64_t col = a.index_pos[p];
+    const bool bad_col = col < 0 || col >= a.C;
+    if (bad_col) col = 0;
     prep_one_row<DT>(a.txt, col, p, a.D, a.rinv_p, a.norm_p, a.pos0, a.pos1);
     if (lane == 0) {
-      int64_t row = a.labels_t[col];
-      a.lab_t[p] = (row >= 0 && row < a.R) ? (int)row : -1;
+      const int64_t row = a.labels_t[col];
+      a.lab_t[p] = (bad_col || row < 0 || row >= a.R) ? kLabBad : (int)row;
       a.lab_logit_t[p] = 0.f;
-      a.col_pos[col] = p;
     }
   }
 }
@@ -585,42 +600,62 @@ __global__ void instance_bwd_kernel(InstArgs a) {
       a.dtxt_hat[c * a.D + d] = s * dl * ri * In<DT>::ld(xi + d);
     }
   }
-  if (lane == 0) a.dls_part[lb] = dls / kLn2;   // sum_dls_kernel multiplies by ln2
+  if (lane == 0) a.dls_part[lb] = dls / kLn2;   // the final reduction multiplies by ln2
 }
 
 struct ItemArgs {
-  const void* img; const void* txt;
-  const float* logit_scale;
-  const int64_t* labels_i; const int64_t* labels_t; const int64_t* index_pos;
-  const float *rinv_i, *rinv_t;
+  const int64_t* index_pos;
   const float2* part_i; int nblk_i;
   const float2* part_t; int nblk_t;
-  int R, C, P, D;
-  int64_t col_offset;
+  int R, C, P;
   float4* row_part;   // [R]  (max2, sum2, label logit if the label column is local, 0)
   const float* lab_logit_i;  // [R]
   const float* lab_logit_t;  // [P]
+  const int* lab_local;      // [R]
+  const int* lab_t;          // [P]
+  int* col_pos;              // [C] description -> positive slot (-1 from prep_all_kernel)
   float* lse2_col;    // [P]
   float* item_t;      // [P]  colLSE - positive logit
   int image_side;     // 0: the image-side rows were produced elsewhere (over-instance mode)
+  int* status;
+  float* sums;        // [4] {sum_p item_t, P, 0, 0}
+  // world == 1: the last block also finishes the forward (ce_contrastive_fwd_finish's work)
+  float* lse2_row; float* loss_i; float* loss_t;
 };
 
-// One warp per item: rows 0..R-1 (image side), then P text-side items.
-template <int DT>
-__global__ void fwd_items_kernel(ItemArgs a) {
+__device__ __forceinline__ double block_sum_double(double s, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+  return t;
+}
+
+// One warp per item: rows 0..R-1 (image side), then P text-side items.  The block that finishes
+// last reduces the text-side items in a fixed order (and, on one GPU, emits both losses): three
+// launches of the chain in one.
+__global__ void __launch_bounds__(256) fwd_items_kernel(ItemArgs a) {
   int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
+  int err = 0;
   if (it < a.R) {
-    if (!a.image_side) return;
-    int r = it;
-    float m = -INFINITY, l = 0.f;
-    for (int j = lane; j < a.nblk_i; j += 32) {
-      float2 pr = a.part_i[(int64_t)r * a.nblk_i + j];
-      float mn = fmaxf(m, pr.x);
-      if (mn != -INFINITY) { l = l * ex2(m - mn) + pr.y * ex2(pr.x - mn); m = mn; }
+    if (a.image_side) {
+      int r = it;
+      float m = -INFINITY, l = 0.f;
+      for (int j = lane; j < a.nblk_i; j += 32) {
+        float2 pr = a.part_i[(int64_t)r * a.nblk_i + j];
+        float mn = fmaxf(m, pr.x);
+        if (mn != -INFINITY) { l = l * ex2(m - mn) + pr.y * ex2(pr.x - mn); m = mn; }
+      }
+      warp_merge_ml(m, l);
+      if (lane == 0) {
+        a.row_part[r] = make_float4(m, l, a.lab_logit_i[r], 0.f);
+        if (a.lab_local[r] == kLabBad) err |= kErrLabelImage;
+      }
     }
-    warp_merge_ml(m, l);
-    if (lane == 0) a.row_part[r] = make_float4(m, l, a.lab_logit_i[r], 0.f);
   } else if (it < a.R + a.P) {
     int p = it - a.R;
     float m = -INFINITY, l = 0.f;
@@ -634,29 +669,43 @@ __global__ void fwd_items_kernel(ItemArgs a) {
     if (lane == 0) {
       a.lse2_col[p] = lse2;
       a.item_t[p] = lse2 * kLn2 - a.lab_logit_t[p];
+      if (a.lab_t[p] == kLabBad) err |= kErrIndexPos;
+      else if (atomicExch(&a.col_pos[a.index_pos[p]], p) != -1) err |= kErrDupPos;
     }
   }
-}
-
-// sums = {sum_p item_t[p], P, 0, 0}; one block, fixed order.
-__global__ void __launch_bounds__(1024) sum_items_kernel(const float* item_t, int P, float* sums) {
-  __shared__ double sh[32];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < P; i += 1024) s += (double)item_t[i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  if (err) atomicOr(&a.status[0], err);
+  // ---- last block: fixed-order reductions ------------------------------------------------------
+  __shared__ int s_last;
+  __shared__ double sh[8];
+  __threadfence();
   __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&a.status[1], 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double s = 0.0;
+  for (int i = threadIdx.x; i < a.P; i += blockDim.x) s += (double)__ldcg(a.item_t + i);
+  const double st = block_sum_double(s, sh);
+  const bool bad = __ldcg(a.status) != 0;
+  if (threadIdx.x == 0) { a.sums[0] = (float)st; a.sums[1] = (float)a.P; a.sums[2] = 0.f; a.sums[3] = 0.f; }
+  if (a.loss_i == nullptr) return;
+  double acc = 0.0;
+  for (int r = threadIdx.x; r < a.R; r += blockDim.x) {
+    const float4 pr = __ldcg(a.row_part + r);
+    const float lse2 = pr.x + log2f(pr.y);
+    a.lse2_row[r] = lse2;
+    acc += (double)(lse2 * kLn2 - pr.z);
+  }
+  const double ti = block_sum_double(acc, sh);
   if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < 32; ++i) t += sh[i];
-    sums[0] = (float)t; sums[1] = (float)P; sums[2] = 0.f; sums[3] = 0.f;
+    *a.loss_i = bad ? __int_as_float(0x7fc00000) : (float)(ti / (double)a.R);
+    *a.loss_t = bad ? __int_as_float(0x7fc00000) : (float)(st / (double)a.P);
   }
 }
 
 // Merge the per-rank row statistics, emit both losses and the global base-2 row LSE.
 __global__ void __launch_bounds__(1024) fwd_finish_kernel(const float* row_part_all, const float* sums_all,
-                                                          int64_t rank_stride, int world, int R,
+                                                          int64_t rank_stride, int world, int R, const int* status,
                                                           float* lse2_row, float* loss_i, float* loss_t) {
   __shared__ double sh[32];
   double acc = 0.0;
@@ -679,36 +728,39 @@ __global__ void __launch_bounds__(1024) fwd_finish_kernel(const float* row_part_
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < 32; ++i) t += sh[i];
-    *loss_i = (float)(t / (double)R);
+    const bool bad = *status != 0;      // clamped input indices: fail loudly (NaN), like the reference's IndexError
+    *loss_i = bad ? __int_as_float(0x7fc00000) : (float)(t / (double)R);
     double st = 0.0, sp = 0.0;
     for (int w = 0; w < world; ++w) { st += (double)sums_all[w * rank_stride]; sp += (double)sums_all[w * rank_stride + 1]; }
-    *loss_t = (float)(st / sp);
-  }
-}
-
-__global__ void __launch_bounds__(1024) sum_dls_kernel(const float* part, int n, float* out) {
-  __shared__ double sh[32];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += 1024) s += (double)part[i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < 32; ++i) t += sh[i];
-    *out = (float)(t * (double)kLn2);
+    *loss_t = bad ? __int_as_float(0x7fc00000) : (float)(st / sp);
   }
 }
 
 // dx = (d - x^ (x^ . d)) / |x|, one warp per row (model_clip.py:496-497 backward).
 // `extra` (optional): per-row index into a second fp32 matrix whose row is added to d first (the
 // text-side gradient of a positive description).
+// Block 0 also reduces the gradient GEMMs' dlogit_scale partials (fixed order, double) when asked to:
+// the chain's last kernel absorbs what used to be a launch of its own.
 template <int DT, int kMaxIter>
-__global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, int D, void* out,
-                                     const int* extra_idx, const float* extra) {
+__global__ void __launch_bounds__(256) normalize_bwd_kernel(const void* xin, const float* d, int rows, int D, void* out,
+                                     const int* extra_idx, const float* extra,
+                                     const float* dls_part, int n_dls, float* dls_out) {
   using T = typename In<DT>::type;
   constexpr int V = In<DT>::kVec;
+  if (blockIdx.x == 0 && dls_out != nullptr) {
+    __shared__ double sh[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_dls; i += 256) s += (double)dls_part[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < 8; ++i) t += sh[i];
+      *dls_out = (float)(t * (double)kLn2);
+    }
+  }
   int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -792,14 +844,15 @@ __global__ void normalize_bwd_kernel(const void* xin, const float* d, int rows, 
 
 template <int DT>
 int launch_normalize_bwd(const void* x, const float* d, int rows, int D, void* out, const int* extra_idx,
-                         const float* extra, cudaStream_t st) {
+                         const float* extra, cudaStream_t st, const float* dls_part = nullptr, int n_dls = 0,
+                         float* dls_out = nullptr) {
   const int per_iter = 32 * In<DT>::kVec;
   const int iters = (D + per_iter - 1) / per_iter;
   const int blocks = (int)(((int64_t)rows * 32 + 255) / 256);
-  if (iters <= 1) normalize_bwd_kernel<DT, 1><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra);
-  else if (iters == 2) normalize_bwd_kernel<DT, 2><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra);
-  else if (iters == 3) normalize_bwd_kernel<DT, 3><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra);
-  else normalize_bwd_kernel<DT, 4><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra);
+  if (iters <= 1) normalize_bwd_kernel<DT, 1><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra, dls_part, n_dls, dls_out);
+  else if (iters == 2) normalize_bwd_kernel<DT, 2><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra, dls_part, n_dls, dls_out);
+  else if (iters == 3) normalize_bwd_kernel<DT, 3><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra, dls_part, n_dls, dls_out);
+  else normalize_bwd_kernel<DT, 4><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra, dls_part, n_dls, dls_out);
   CE_LAUNCH_CHECK();
   return CE_OK;
 }
@@ -815,6 +868,7 @@ struct CtrWs {
   float2 *part_i, *part_t;
   float4* row_part;
   float *sums, *dls_part;
+  int* status;
   void *img_p[2], *txt_p[2], *pos_p[2];
   void* G[2];      // image-side gradient matrix [R, ldg]
   void* Gt[2];     // text-side  gradient matrix [P, ldgt]
@@ -845,6 +899,7 @@ CtrWs carve(void* base, int R, int C, int P, int D, int dtype) {
   w.part_t = cv.take<float2>((size_t)P * w.nblk_t * 2);
   w.row_part = cv.take<float4>(R);
   w.sums = cv.take<float>(4);
+  w.status = cv.take<int>(4);
   w.dls_part = cv.take<float>((size_t)(w.tiles_g + w.tiles_gt) * 8 + (size_t)C);
   w.logits_bt = cv.take<float>((size_t)C);
   if (dtype == CE_F32) {
@@ -927,11 +982,10 @@ template <int DT>
 int fwd_partial_impl(const void* img, const void* txt, const float* ls, const void* labels_i_v,
                      const int64_t* labels_t, const int64_t* index_pos, int R, int C, int P, int D,
                      int64_t col_offset, int mode, int T, int64_t row_offset, float* row_part,
-                     float* sums, CtrWs& w, cudaStream_t st) {
+                     float* sums, float* loss_i, float* loss_t, int64_t label_hi, CtrWs& w, cudaStream_t st) {
   constexpr bool TF = DT == CE_F32;
   constexpr int BN = s_bn<DT>();
   const int64_t* labels_i = mode == 0 ? reinterpret_cast<const int64_t*>(labels_i_v) : nullptr;
-  CE_CUDA_TRY(cudaMemsetAsync(w.col_pos, 0xff, sizeof(int) * (size_t)C, st));   // -1 everywhere
   {
     PrepAllArgs pa{};
     pa.img = img; pa.txt = txt; pa.labels_i = labels_i; pa.labels_t = labels_t; pa.index_pos = index_pos;
@@ -943,6 +997,7 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     pa.pos0 = w.pos_p[0]; pa.pos1 = w.pos_p[1];
     pa.lab_local = w.lab_local; pa.lab_t = w.lab_t; pa.col_pos = w.col_pos;
     pa.lab_logit_i = w.lab_logit_i; pa.lab_logit_t = w.lab_logit_t;
+    pa.status = w.status; pa.label_hi = label_hi;
     const int64_t warps = (int64_t)R + C + P;
     prep_all_kernel<DT><<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(pa);
     CE_LAUNCH_CHECK();
@@ -965,13 +1020,16 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     typename EpiStats<BN>::Params ep{w.rinv_p, w.rinv_i, ls, w.part_t, P, R, w.nblk_t, w.lab_t, w.lab_logit_t};
     CE_TRY((launch_gemm_auto<TF, BN, EpiStats<BN>>(1, op, oi, D, ep, st)));
   }
-  ItemArgs ia{img, txt, ls, labels_i, labels_t, index_pos, w.rinv_i, w.rinv_t, w.part_i, 2 * w.nblk_i,
-              w.part_t, 2 * w.nblk_t, R, C, P, D, col_offset, reinterpret_cast<float4*>(row_part),
-              w.lab_logit_i, w.lab_logit_t, w.lse2_col, w.item_t, mode == 0 ? 1 : 0};
+  // (max, sum) merge of the per-tile statistics, the positives' slots, the text-side sum and -- on one
+  // GPU (loss_i != nullptr) -- both losses and the row LSE: one launch
+  ItemArgs ia{};
+  ia.index_pos = index_pos; ia.part_i = w.part_i; ia.nblk_i = 2 * w.nblk_i; ia.part_t = w.part_t; ia.nblk_t = 2 * w.nblk_t;
+  ia.R = R; ia.C = C; ia.P = P; ia.row_part = reinterpret_cast<float4*>(row_part);
+  ia.lab_logit_i = w.lab_logit_i; ia.lab_logit_t = w.lab_logit_t; ia.lab_local = w.lab_local; ia.lab_t = w.lab_t;
+  ia.col_pos = w.col_pos; ia.lse2_col = w.lse2_col; ia.item_t = w.item_t; ia.image_side = mode == 0 ? 1 : 0;
+  ia.status = w.status; ia.sums = sums; ia.lse2_row = w.lse2_row; ia.loss_i = loss_i; ia.loss_t = loss_t;
   int blocks = ((R + P) * 32 + 255) / 256;
-  fwd_items_kernel<DT><<<blocks, 256, 0, st>>>(ia);
-  CE_LAUNCH_CHECK();
-  sum_items_kernel<<<1, 1024, 0, st>>>(w.item_t, P, sums);
+  fwd_items_kernel<<<blocks, 256, 0, st>>>(ia);
   CE_LAUNCH_CHECK();
   return CE_OK;
 }
@@ -1056,8 +1114,6 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     const GemmOut go{w.Gt[0], P, (int)w.ldgt, w.ldgt};
     CE_TRY((launch_gemm_auto<TF, BN, EpiGrad<BN, TF>>(2, op, oi, D, ep, st, TF ? nullptr : &go)));
   }
-  sum_dls_kernel<<<1, 1024, 0, st>>>(w.dls_part, n_dls, dls_out);
-  CE_LAUNCH_CHECK();
   GemmOperand tB = operand<DT>(txt, w.txt_p, D, D, 1);          // [K = C, N = D]
   GemmOperand iB = operand<DT>(img, w.img_p, D, D, 1);          // [K = R, N = D]
   GemmOperand pB = operand<DT>(w.pos_p[0], w.pos_p, D, D, 1);   // [K = P, N = D]
@@ -1069,7 +1125,7 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
   if (mode == 0)
     CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, C, w.ldg, 1), iB, R, w.dtxt_hat, D, w.norm_t, ls, false, st)));
   CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, P, w.ldgt, 0), iB, R, w.dpos_hat, D, w.norm_p, ls, false, st)));
-  CE_TRY((launch_normalize_bwd<DT>(txt, w.dtxt_hat, C, D, dtxt, w.col_pos, w.dpos_hat, st)));
+  CE_TRY((launch_normalize_bwd<DT>(txt, w.dtxt_hat, C, D, dtxt, w.col_pos, w.dpos_hat, st, w.dls_part, n_dls, dls_out)));
   return CE_OK;
 }
 
@@ -1104,8 +1160,10 @@ extern "C" int ce_contrastive_fwd_partial(const void* img, const void* txt, cons
   CtrWs w = carve(workspace, R, C, P, D, dtype);
   if (workspace_bytes < w.bytes) return fail(CE_ERR_WORKSPACE, "contrastive: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == CE_F32) return fwd_partial_impl<CE_F32>(img, txt, logit_scale, labels_i, labels_t, index_pos, R, C, P, D, col_offset, image_loss, T, row_offset, row_part, sums, w, st);
-  return fwd_partial_impl<CE_BF16>(img, txt, logit_scale, labels_i, labels_t, index_pos, R, C, P, D, col_offset, image_loss, T, row_offset, row_part, sums, w, st);
+  // sharded call: the label columns may belong to any rank, only their sign is checked here
+  const int64_t label_hi = INT64_MAX;
+  if (dtype == CE_F32) return fwd_partial_impl<CE_F32>(img, txt, logit_scale, labels_i, labels_t, index_pos, R, C, P, D, col_offset, image_loss, T, row_offset, row_part, sums, nullptr, nullptr, label_hi, w, st);
+  return fwd_partial_impl<CE_BF16>(img, txt, logit_scale, labels_i, labels_t, index_pos, R, C, P, D, col_offset, image_loss, T, row_offset, row_part, sums, nullptr, nullptr, label_hi, w, st);
 }
 
 extern "C" int ce_contrastive_fwd_finish(const float* row_part_all, const float* sums_all,
@@ -1119,7 +1177,7 @@ extern "C" int ce_contrastive_fwd_finish(const float* row_part_all, const float*
   CtrWs w = carve(workspace, R, C, P, D, dtype);
   if (workspace_bytes < w.bytes) return fail(CE_ERR_WORKSPACE, "contrastive: workspace too small");
   fwd_finish_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      row_part_all, sums_all, rank_stride, world, R, w.lse2_row, loss_i, loss_t);
+      row_part_all, sums_all, rank_stride, world, R, w.status, w.lse2_row, loss_i, loss_t);
   CE_LAUNCH_CHECK();
   return CE_OK;
 }
@@ -1170,12 +1228,12 @@ extern "C" int ce_contrastive_fwd(const void* img, const void* txt, const float*
   CE_TRY(check_common(B, BT, P, D, dtype, img, txt));
   CtrWs w = carve(workspace, B, BT, P, D, dtype);
   if (workspace_bytes < w.bytes) return fail(CE_ERR_WORKSPACE, "contrastive: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
-  CE_TRY(ce_contrastive_fwd_partial(img, txt, logit_scale, labels_i, labels_t, index_pos, B, BT, P, D, 0,
-                                    image_loss, B > 0 ? BT / B : 1, 0, dtype,
-                                    reinterpret_cast<float*>(w.row_part), w.sums, workspace,
-                                    workspace_bytes, stream));
-  return ce_contrastive_fwd_finish(reinterpret_cast<const float*>(w.row_part), w.sums, 0, 1, B, BT, P, D,
-                                   dtype, loss_i, loss_t, workspace, workspace_bytes, stream);
+  const int T = B > 0 ? BT / B : 1;
+  CE_TRY(check_mode(image_loss, T, BT, 0, B));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* rp = reinterpret_cast<float*>(w.row_part);
+  if (dtype == CE_F32) return fwd_partial_impl<CE_F32>(img, txt, logit_scale, labels_i, labels_t, index_pos, B, BT, P, D, 0, image_loss, T, 0, rp, w.sums, loss_i, loss_t, BT, w, st);
+  return fwd_partial_impl<CE_BF16>(img, txt, logit_scale, labels_i, labels_t, index_pos, B, BT, P, D, 0, image_loss, T, 0, rp, w.sums, loss_i, loss_t, BT, w, st);
 }
 
 extern "C" int ce_contrastive_bwd(const void* img, const void* txt, const float* logit_scale,

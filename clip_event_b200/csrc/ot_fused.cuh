@@ -1,0 +1,36 @@
+// Fused, shared-memory-resident OT kernel (csrc/ot_fused.cu): launcher interface.
+#pragma once
+
+#include <stdlib.h>
+
+#include "ce_common.cuh"
+
+namespace ce {
+
+struct OtFusedArgs {
+  const void* txt;            // [B, M, D] bf16, sample stride txt_bs elements
+  const void* img;            // [B, N, D] bf16 (after the whole-image slot), sample stride img_bs
+  int64_t txt_bs, img_bs;
+  const void* txt_mask;
+  const void* img_mask;
+  int64_t txt_ms, img_ms;
+  int mask_kind;
+  int B, M, N, D;
+  float beta, eps, scale;
+  int iters, k;
+  float* dist;                // [B]
+  void* dtxt;                 // nullable (forward only): same layout as txt
+  void* dimg;                 // same layout as img
+  void* dslot0;               // nullable: [B] rows of D elements, stride img_bs, zero-filled
+  int slots;                  // filled in by the launcher
+  int poll_mode;              // debug (CE_OT_POLL)
+  long long* trace;           // debug timeline buffer (CE_OT_TRACE_PTR), normally null
+};
+
+// bf16, M <= 16, N <= 64, D a multiple of 128 up to 768, and at least two samples fit in shared memory
+bool ot_fused_supported(int M, int N, int D, int dtype);
+int ot_fused_slots(int M, int N, int D);
+size_t ot_fused_smem_bytes(int M, int N, int D, int slots);
+int launch_ot_fused(OtFusedArgs a, cudaStream_t st);
+
+}  // namespace ce
