@@ -120,46 +120,304 @@ def make_inputs(w, dtype, lo, hi):
     return host, ls
 
 
+def config_dict(w, world, dtype_name):
+    """Workload description: the SAME dict in both arms (`--impl reference` and the B200 arm)."""
+    return {"workload": "%s: %s" % (w.name, WORKLOAD_TEXT[w.name]), "global_batch": w.B,
+            "descriptions_per_image": w.T, "embed_dim": w.D, "ot_nodes": "%dx%d" % (w.M, w.N), "ipot_iters": w.iters,
+            "ot_masks": "ragged (prefix lengths U{1..})", "logit_scale": "ln(1/0.07)", "n_gpus": world,
+            "parallelism": "B200 arm: global batch sharded over the ranks, column-sharded global negatives; "
+                           "reference arm: one CPU process, full batch",
+            "l2": "inputs (embeddings + node sets, bf16) exceed the 126 MB L2 for c3/c4; smaller workloads get a "
+                  "512 MB L2-flush write between timed steps"}
+
+
+class CpuLossHead:
+    """The reference's loss head on the host cores: the UNMODIFIED modules (oracle/_ref copy written by
+    oracle/make_ref.sh, kind "reference"), or the oracle port when the copy is absent (kind "port").
+    A step is the FULL batch of the workload, fwd + bwd, as engine.py:48-67,88 runs it."""
+
+    def __init__(self, w):
+        from oracle import ref_loader
+        self.w = w
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.img, self.txt, self.ls = syn.contrastive_inputs(w.B, w.T, w.D, 0, "trained")
+        self.lpi, self.lpt, self.idx = syn.contrastive_labels(w.B, w.T)
+        self.etxt, self.obj, self.tnum, self.onum = syn.ot_inputs(w.B, w.M, w.N, w.D, 0, "ragged")
+        if ref_loader.available():
+            self.kind = "reference"
+            self.head = ref_loader.ReferenceLossHead("ce")
+            self.source = os.path.relpath(ref_loader.source_dir(), ROOT) if ref_loader.source_dir().startswith(ROOT) else ref_loader.source_dir()
+        else:
+            from oracle import clip_event_oracle as orc
+            self.kind, self.head, self.orc, self.source = "port", None, orc, "oracle/clip_event_oracle.py"
+
+    def step(self):
+        if self.head is not None:
+            losses, _ = self.head.step(self.img, self.txt, self.ls, self.lpi, self.lpt, self.idx, self.etxt, self.obj,
+                                       self.tnum, self.onum)
+        else:
+            losses, _ = self.orc.loss_head_step(self.img, self.txt, self.ls, self.lpi, self.lpt, self.idx, self.etxt,
+                                                self.obj, self.tnum, self.onum)
+        return losses
+
+    def time(self, steps, warmup):
+        for _ in range(warmup):
+            self.step()
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            self.step()
+            times.append(time.perf_counter() - t0)
+        return times
+
+    def describe(self, steps, warmup):
+        return ("full batch (%d images x %d descriptions, OT on all %d samples) through %s (%s), fp32, torch %d threads; "
+                "%d warm-up + %d timed steps" % (self.w.B, self.w.B * self.w.T, self.w.B, self.source,
+                                                 "the reference's own CriterionContrastive / CriterionAlignment / model_ot, unmodified"
+                                                 if self.kind == "reference" else "line-by-line port", torch.get_num_threads(),
+                                                 warmup, steps))
+
+
 def run_reference(args, w):
-    """--impl reference: the reference algorithm (oracle port, PyTorch CPU) on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import clip_event_oracle as orc
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    img, txt, ls = syn.contrastive_inputs(w.B, w.T, w.D, 0, "trained")
-    etxt, obj, tnum, onum = syn.ot_inputs(w.B, w.M, w.N, w.D, 0, "ragged")
-    # bounded sample: a row block sized so that the whole run (warm-up + steps) is ~2 minutes of
-    # host time; the same block selection as the cpu_baseline leg of the B200 arm
-    rows = min(w.B, 64)
-    t0 = time.perf_counter()
-    orc.loss_head_rowblock_step(img, txt, ls, w.T, (0, rows), etxt, obj, tnum, onum)
-    first = time.perf_counter() - t0
-    per_step_budget = min(4.0, 120.0 / max(args.steps + args.warmup, 1))
-    rows = int(max(16, min(w.B, rows * per_step_budget / max(first, 1e-3))))
-
-    def step():
-        orc.loss_head_rowblock_step(img, txt, ls, w.T, (0, rows), etxt, obj, tnum, onum)
-
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    value = rows / dt
-    sample = "%d-image row block of the %d-image batch: scored against all %d descriptions / %d images, OT on the block" % (
-        rows, w.B, w.B * w.T, w.B)
+    cpu = CpuLossHead(w)
+    times = cpu.time(args.steps, args.warmup)
+    dt = sum(times) / len(times)
+    value = w.B / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (w.name, WORKLOAD_TEXT[w.name]), "global_batch": w.B},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": sample},
+        "config": config_dict(w, args.gpus, "f32"),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cpu.cores, "kind": cpu.kind,
+                         "sample": cpu.describe(args.steps, args.warmup),
+                         "ms_per_step_median": statistics.median(times) * 1e3},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), flush=True)
+
+
+class Harness:
+    """One workload on this rank's GPU: device-resident inputs, the product's one-call step
+    (clip_event_b200.LossHeadStep = engine.py:48-67 + 88), CUDA-graph replay, CUDA-event timing."""
+
+    def __init__(self, w, dtype, world, rank, dev, use_graph=True):
+        import clip_event_b200 as ce
+        from clip_event_b200 import distributed as cd
+        self.w, self.dtype, self.world, self.rank, self.dev = w, dtype, world, rank, dev
+        self.esz = 2 if dtype == torch.bfloat16 else 4
+        lo, hi = cd.shard_bounds(w.B, world, rank)
+        self.lo, self.hi, self.b = lo, hi, hi - lo
+        self.host, self.ls_init = make_inputs(w, dtype, lo, hi)
+        self.static = {k: v.to(dev) for k, v in self.host.items()}
+        # labels as the reference's collate_fn builds them on each rank (dataset_voa.py:617-663)
+        self.lpi, self.lpt, self.idx = (t.to(dev) for t in syn.contrastive_labels(self.b, w.T))
+        self.head = ce.ClipEventHead().to(dev)
+        self.step_mod = ce.LossHeadStep(self.head, group=True if world > 1 else None, ddp_average=False)
+        self.leaves = {k: self.static[k].requires_grad_(True) for k in ("img", "txt", "etxt", "obj")}
+        self.losses_out = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.use_graph = use_graph
+        self.in_bytes = sum(self.static[k].numel() * self.static[k].element_size() for k in ("img", "txt", "etxt", "obj"))
+        self.flush = None
+        if self.in_bytes < 256 * 1024 * 1024:
+            self.flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step(self, static=None, leaves=None, losses_out=None):
+        static = self.static if static is None else static
+        leaves = self.leaves if leaves is None else leaves
+        losses_out = self.losses_out if losses_out is None else losses_out
+        for t in leaves.values():
+            t.grad = None
+        self.head.logit_scale.grad = None
+        loss_dict = self.step_mod(leaves["img"], leaves["txt"], self.lpi, self.lpt, self.idx, leaves["etxt"], leaves["obj"],
+                                  static["tnum"], static["onum"])
+        total = sum(loss_dict.values())                      # engine.py:67, in the losses' own dtype
+        total.backward()                                     # engine.py:88
+        losses_out.copy_(torch.stack([loss_dict["loss_i"], loss_dict["loss_t"], loss_dict["loss_ot"]]).float())
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def capture(self, fn):
+        """Replayable CUDA graph of fn (NCCL included: thread-local capture keeps the watchdog thread legal)."""
+        if not self.use_graph:
+            return fn, False
+        try:
+            s_ = torch.cuda.Stream()
+            s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                fn()
+            torch.cuda.current_stream().wait_stream(s_)
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, capture_error_mode="thread_local"):
+                fn()
+            torch.cuda.synchronize()
+            return g_.replay, True
+        except Exception as e:  # pragma: no cover
+            torch.cuda.synchronize()
+            if self.rank == 0:
+                print("note: CUDA graph capture failed (%s); timing eager launches" % str(e)[:200], file=sys.stderr)
+            return fn, False
+
+    def timed_loop(self, fn, steps, warmup):
+        for _ in range(warmup):
+            if self.flush is not None:
+                self.flush.zero_()
+            fn()
+        self.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s, e in evs:
+            if self.flush is not None:
+                self.flush.zero_()
+            s.record()
+            fn()
+            e.record()
+        self.barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs) / steps
+        t = torch.tensor([ms], device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def chains(self, n_seg):
+        """CUDA-event time of each chain alone (graph replay): the rooflines' denominators."""
+        from clip_event_b200 import distributed as cd
+        from clip_event_b200 import functional as F_
+        lv, st, w = self.leaves, self.static, self.w
+
+        def chain_contrastive():
+            for t in (lv["img"], lv["txt"]):
+                t.grad = None
+            self.head.logit_scale.grad = None
+            if self.world > 1:
+                lpi, lpt, idx = cd.global_labels_for_rank(self.b, w.T, self.world, self.rank, device=self.dev)
+                li, lt = cd.global_contrastive(lv["img"], lv["txt"], self.head.logit_scale, None, lpt, idx)
+            else:
+                li, lt = F_.contrastive_over_batch(lv["img"], lv["txt"], self.head.logit_scale, self.lpi, self.lpt, self.idx)
+            (li + lt).backward()
+
+        def chain_ot():
+            for t in (lv["etxt"], lv["obj"]):
+                t.grad = None
+            loss, _ = F_.ot_alignment(lv["etxt"], lv["obj"], st["tnum"], st["onum"])
+            loss.backward()
+
+        ms_con = self.timed_loop(self.capture(chain_contrastive)[0], n_seg, 3)
+        ms_ot = self.timed_loop(self.capture(chain_ot)[0], n_seg, 3)
+        return ms_con, ms_ot
+
+    def rooflines(self, ms_con, ms_ot, peaks, traffic_tag=None):
+        w = self.w
+        flops = algorithmic_work(w, self.esz, w.B, self.b)           # per rank: all B rows x local columns
+        ot_bytes = 2.0 * (w.M + w.N) * w.D * self.esz * self.b
+        bf16 = self.dtype == torch.bfloat16
+        tensor_peak = peaks["bf16_tflops"] * (1.0 if bf16 else 0.5)
+        roof_gemm = {"kernel": "umma_gemm_kernel chain (ce_contrastive_fwd + ce_contrastive_bwd)", "bound": "tensor",
+                     "achieved": flops / (ms_con * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
+                     "frac": flops / (ms_con * 1e-3) / 1e12 / tensor_peak, "traffic": None, "ms": ms_con,
+                     "peak_source": peaks["source"] + (" bf16 burst" if bf16 else " bf16 burst / 2 (tf32; 3 products per flop in fp32 mode)")}
+        roof_ot = {"kernel": "ce_ot_fwd_bwd chain (OT cost + IPOT + gradient)", "bound": "hbm",
+                   "achieved": ot_bytes / (ms_ot * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                   "frac": ot_bytes / (ms_ot * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "ms": ms_ot,
+                   "peak_source": peaks["source"] + " copy bandwidth"}
+        if traffic_tag is not None and self.world == 1:
+            for rnd in ("r02", "r01"):
+                tpath = os.path.join(ROOT, "profiles", "%s_traffic_%s.json" % (rnd, traffic_tag))
+                if os.path.exists(tpath):
+                    with open(tpath) as f:
+                        tr = json.load(f)
+                    roof_gemm["traffic"] = tr.get("gemm_chain_bytes_per_step")
+                    roof_ot["traffic"] = tr.get("ot_chain_bytes_per_step")
+                    roof_gemm["traffic_source"] = roof_ot["traffic_source"] = "profiles/" + os.path.basename(tpath)
+                    break
+        return roof_gemm, roof_ot
+
+
+def dist_parity(world, rank, dev, dtype):
+    """N > 1: one step of the sharded loss head against (a) the single-GPU CUDA path on the full batch
+    (bench workload size, same dtype) and (b) the fp64 closed-form oracle at a reduced size.  Every rank
+    checks its own slices; the worst relative error over the ranks is reported."""
+    import torch.distributed as dist
+    import clip_event_b200 as ce
+    from clip_event_b200 import distributed as cd
+    from oracle import clip_event_oracle as orc
+
+    def rel(a, b):
+        a, b = a.detach().double().flatten(), b.detach().double().flatten()
+        return float(((a - b).norm() / b.norm().clamp_min(1e-30)).item())
+
+    def run_pair(B, T, D, M, N, seed, with_oracle):
+        img, txt, ls = syn.contrastive_inputs(B, T, D, seed, "trained", dtype=dtype)
+        etxt, obj, tnum, onum = syn.ot_inputs(B, M, N, D, seed + 1, "ragged", dtype=dtype)
+        lo, hi = cd.shard_bounds(B, world, rank)
+        b = hi - lo
+        lpi, lpt, idx = (t.to(dev) for t in syn.contrastive_labels(b, T))
+        head = ce.ClipEventHead().to(dev)
+        sh = ce.LossHeadStep(head, group=True, ddp_average=False)
+        lv = dict(img=img[lo:hi], txt=txt[lo * T:hi * T], etxt=etxt[lo:hi], obj=obj[lo:hi])
+        lv = {k: v.to(dev).requires_grad_(True) for k, v in lv.items()}
+        ld = sh(lv["img"], lv["txt"], lpi, lpt, idx, lv["etxt"], lv["obj"], tnum[lo:hi].to(dev), onum[lo:hi].to(dev))
+        sum(ld.values()).backward()
+        # single-GPU CUDA path on the whole batch (every rank computes it; it fits one GPU)
+        head1 = ce.ClipEventHead().to(dev)
+        s1 = ce.LossHeadStep(head1)
+        fl = dict(img=img, txt=txt, etxt=etxt, obj=obj)
+        fl = {k: v.to(dev).requires_grad_(True) for k, v in fl.items()}
+        gl = [t.to(dev) for t in syn.contrastive_labels(B, T)]
+        ld1 = s1(fl["img"], fl["txt"], gl[0], gl[1], gl[2], fl["etxt"], fl["obj"], tnum.to(dev), onum.to(dev))
+        sum(ld1.values()).backward()
+        torch.cuda.synchronize()
+        errs = {
+            "loss_i": abs(ld["loss_i"].item() - ld1["loss_i"].item()) / max(abs(ld1["loss_i"].item()), 1e-30),
+            "loss_t": abs(ld["loss_t"].item() - ld1["loss_t"].item()) / max(abs(ld1["loss_t"].item()), 1e-30),
+            "loss_ot": abs(ld["loss_ot"].item() - ld1["loss_ot"].item()) / max(abs(ld1["loss_ot"].item()), 1e-30),
+            "dimg": rel(lv["img"].grad, fl["img"].grad[lo:hi]), "dtxt": rel(lv["txt"].grad, fl["txt"].grad[lo * T:hi * T]),
+            "detxt": rel(lv["etxt"].grad, fl["etxt"].grad[lo:hi]), "dobj": rel(lv["obj"].grad, fl["obj"].grad[lo:hi]),
+            "dls": abs(head.logit_scale.grad.item() - head1.logit_scale.grad.item()) / max(1.0, abs(head1.logit_scale.grad.item())),
+        }
+        if with_oracle:
+            glc = syn.contrastive_labels(B, T)
+            ri, rt, rdi, rdt, rdls = orc.contrastive_closed_form(img.double(), txt.double(), ls.double(), glc[0], glc[1], glc[2])
+            tp, ip = tnum == 0, onum[:, 1:] == 0
+            d_ref, dx_ref, dy_ref = orc.ot_closed_form_grads(etxt.double(), obj.double()[:, 1:], tp, ip,
+                                                             torch.full((B,), 0.01, dtype=torch.float64))
+            errs.update({
+                "oracle_loss_i": abs(ld["loss_i"].item() - ri.item()) / abs(ri.item()),
+                "oracle_loss_ot": abs(ld["loss_ot"].item() - 0.01 * d_ref.sum().item()) / abs(0.01 * d_ref.sum().item()),
+                "oracle_dimg": rel(lv["img"].grad.cpu(), rdi[lo:hi]), "oracle_dtxt": rel(lv["txt"].grad.cpu(), rdt[lo * T:hi * T]),
+                "oracle_detxt": rel(lv["etxt"].grad.cpu(), dx_ref[lo:hi]), "oracle_dobj": rel(lv["obj"].grad[:, 1:].cpu(), dy_ref[lo:hi]),
+                "oracle_dls": abs(head.logit_scale.grad.item() - rdls.item()) / max(1.0, abs(rdls.item())),
+            })
+        return errs
+
+    w3 = syn.WORKLOADS["c3"]
+    full = run_pair(w3.B, w3.T, w3.D, w3.M, w3.N, 0, False)          # bench size: sharded vs single-GPU kernels
+    small = run_pair(64 * world, 9, 512, 16, 50, 31, True)            # reduced size: sharded vs fp64 oracle
+    bf16 = dtype == torch.bfloat16
+    loss_tol, grad_tol = (2e-3, 1e-2) if bf16 else (1e-5, 5e-5)
+    out = {}
+    ok = True
+    for tag, errs in (("vs_single_gpu_c3", full), ("vs_oracle_B%d" % (64 * world), small)):
+        keys = sorted(errs)
+        t = torch.tensor([errs[k] for k in keys], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        worst = {k: float(v) for k, v in zip(keys, t.tolist())}
+        out[tag] = {k: float("%.3g" % v) for k, v in worst.items()}
+        for k, v in worst.items():
+            # bf16: the two paths round their gradients to bf16 independently (reduction orders differ)
+            tol = loss_tol if "loss" in k else (1e-2 if "dls" in k and bf16 else (1e-4 if "dls" in k else grad_tol))
+            ok = ok and (v == v) and v <= tol
+    out["tolerance"] = {"loss": loss_tol, "grad": grad_tol}
+    out["ok"] = bool(ok)
+    return out
 
 
 def main():
@@ -172,6 +430,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the c3-fp32 / c4-bf16 secondary lines (N=1)")
+    ap.add_argument("--no-dist-parity", action="store_true")
     args = ap.parse_args()
     w = syn.WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -179,10 +439,7 @@ def main():
         return
 
     import torch.distributed as dist
-    import clip_event_b200 as ce
     from clip_event_b200 import _lib as L
-    from clip_event_b200 import distributed as cd
-    from clip_event_b200 import functional as F_
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,117 +455,34 @@ def main():
     lib = L.load()
     L.check(lib.ce_device_check(), "device check")
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    esz = 2 if args.dtype == "bf16" else 4
     peaks = load_peaks()
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
 
-    lo, hi = cd.shard_bounds(w.B, world, rank)
-    b = hi - lo
-    host, ls_init = make_inputs(w, dtype, lo, hi)
-    static = {k: v.to(dev) for k, v in host.items()}
-    if world > 1:
-        lpi, lpt, idx = cd.global_labels_for_rank(b, w.T, world, rank, device=dev)
-    else:
-        lpi, lpt, idx = (t.to(dev) for t in syn.contrastive_labels(w.B, w.T))
-    head = ce.ClipEventHead().to(dev)
-    crit, crit_ot = ce.CriterionContrastive("ce"), ce.CriterionAlignment()
-    leaves = {k: static[k].requires_grad_(True) for k in ("img", "txt", "etxt", "obj")}
-    losses_out = torch.zeros(3, dtype=torch.float32, device=dev)
-    losses_host = torch.zeros(3, dtype=torch.float32).pin_memory()
-
-    ot_stream = torch.cuda.Stream()
-
-    def step(static=static, leaves=leaves, losses_out=losses_out):
-        """fwd + bwd of the loss head as engine.py:48-67,88 drives it.  The two criteria are
-        independent until the final sum, so the OT criterion is issued on a second stream: its
-        ALU/HBM-bound kernels overlap the tensor-core GEMMs and the NCCL latencies (autograd runs
-        each backward on the stream of its forward)."""
-        for t in leaves.values():
-            t.grad = None
-        head.logit_scale.grad = None
-        main = torch.cuda.current_stream()
-        ot_stream.wait_stream(main)
-        with torch.cuda.stream(ot_stream):
-            if world > 1:
-                loss_ot = cd.sharded_alignment(leaves["etxt"], leaves["obj"], static["tnum"], static["onum"])
-            else:
-                loss_ot = crit_ot(leaves["etxt"], leaves["obj"], static["tnum"], static["onum"])["loss_ot"]
-        if world > 1:
-            li, lt = cd.global_contrastive(leaves["img"], leaves["txt"], head.logit_scale, None, lpt, idx)  # canonical labels
-            loss_dict = {"loss_i": li, "loss_t": lt}
-        else:
-            a, b_ = head(leaves["img"], leaves["txt"])
-            loss_dict = crit(a, b_, lpi, lpt, index_pos=idx, constrastive_overbatch=True)
-        main.wait_stream(ot_stream)
-        loss_dict["loss_ot"] = loss_ot
-        total = sum(loss for loss in loss_dict.values())     # engine.py:67, in the losses' own dtype
-        total.backward()
-        main.wait_stream(ot_stream)
-        losses_out.copy_(torch.stack([loss_dict["loss_i"], loss_dict["loss_t"], loss_dict["loss_ot"]]))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    parity = None
+    if world > 1 and not args.no_dist_parity:
+        parity = dist_parity(world, rank, dev, dtype)
         torch.cuda.synchronize()
+        dist.barrier()
 
+    h = Harness(w, dtype, world, rank, dev, use_graph=not args.no_graph)
     # ---- warm-up (eager), count launches ----------------------------------------------------
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for _ in range(3):
-            step()
+            h.step()
         n0 = lib.ce_debug_launch_count()
-        step()
+        h.step()
         launches_per_step = int(lib.ce_debug_launch_count() - n0)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-
-    graph = None
-    if not args.no_graph:   # the NCCL exchange is captured too (thread-local capture: the NCCL watchdog thread stays legal)
-        try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                step()
-            torch.cuda.synchronize()
-        except Exception as e:  # pragma: no cover
-            graph = None
-            torch.cuda.synchronize()
-            if rank == 0:
-                print("note: CUDA graph capture failed (%s); timing eager launches" % str(e)[:200], file=sys.stderr)
-    run = graph.replay if graph is not None else step
-
-    # inputs (per rank): img+txt+OT nodes; > L2 (126 MB) for c3/c4, otherwise flush L2 between steps
-    in_bytes = sum(static[k].numel() * static[k].element_size() for k in ("img", "txt", "etxt", "obj"))
-    flush = None
-    if in_bytes < 256 * 1024 * 1024:
-        flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def timed_loop(fn, steps, warmup, per_step_host=None):
-        for _ in range(warmup):
-            if flush is not None:
-                flush.zero_()
-            fn()
-        barrier()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for s, e in evs:
-            if flush is not None:
-                flush.zero_()
-            s.record()
-            fn()
-            e.record()
-            if per_step_host is not None:
-                per_step_host()
-        barrier()
-        ms = sum(s.elapsed_time(e) for s, e in evs) / steps
-        t = torch.tensor([ms], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    run, graphed = h.capture(h.step)
 
     # ---- device-resident timing ("value") ---------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_step = timed_loop(run, args.steps, max(args.warmup, 3))
+    ms_step = h.timed_loop(run, args.steps, max(args.warmup, 3))
     # K steps last ~20 ms -- shorter than one nvidia-smi sampling period -- so the same step keeps
     # replaying for 0.6 s more (not timed) while the sampler runs: the clocks line then describes the
     # GPU under exactly this load
@@ -325,31 +499,23 @@ def main():
     # The loop is the one a training loop with a prefetching loader runs: two device input sets, the
     # copy of step i+1 (copy stream) overlapping the kernels of step i; the timed region is the wall
     # clock from the first copy to the last loss landing on the host.
+    host, static, leaves, losses_out = h.host, h.static, h.leaves, h.losses_out
     sets = [(static, leaves, losses_out, run)]
-    if graph is not None:
+    if graphed:
         try:
-            # the second set's warm-up runs on a side stream after the first set's graph exists
-            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
             static_b = {k: v.detach().clone() for k, v in static.items()}
             leaves_b = {k: static_b[k].requires_grad_(True) for k in ("img", "txt", "etxt", "obj")}
             losses_b = torch.zeros(3, dtype=torch.float32, device=dev)
-            step_b = lambda: step(static_b, leaves_b, losses_b)   # noqa: E731
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step_b()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph_b = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph_b, capture_error_mode="thread_local"):
-                step_b()
-            torch.cuda.synchronize()
-            sets.append((static_b, leaves_b, losses_b, graph_b.replay))
+            run_b, ok_b = h.capture(lambda: h.step(static_b, leaves_b, losses_b))
+            if ok_b:
+                sets.append((static_b, leaves_b, losses_b, run_b))
         except Exception as e:  # pragma: no cover
             torch.cuda.synchronize()
             if rank == 0:
                 print("note: second input set not captured (%s); e2e runs unpipelined" % str(e)[:200], file=sys.stderr)
     n_e2e = 3 + min(args.steps, 10)
     losses_e2e = torch.zeros(n_e2e, 3, dtype=torch.float32).pin_memory()
+    losses_host = torch.zeros(3, dtype=torch.float32)
     copy_stream = torch.cuda.Stream()
     main_stream = torch.cuda.current_stream()
     copied = [torch.cuda.Event() for _ in sets]
@@ -372,7 +538,7 @@ def main():
     for ev in consumed:
         ev.record(main_stream)
     e2e_loop(0, 3)                                   # warm-up
-    barrier()
+    h.barrier()
     t0 = time.perf_counter()
     e2e_loop(3, n_e2e)
     e2e_s = torch.tensor([(time.perf_counter() - t0) / (n_e2e - 3)], device=dev)
@@ -384,106 +550,60 @@ def main():
            "d2h_bytes_per_step": 12, "ms_per_step": float(e2e_s.item()) * 1e3,
            "input_sets": len(sets), "steps": n_e2e - 3}
 
-    # ---- per-chain timing for the rooflines (eager, events around each C-ABI chain) -----------
-    def chain_contrastive():
-        for t in (leaves["img"], leaves["txt"]):
-            t.grad = None
-        head.logit_scale.grad = None
-        if world > 1:
-            li, lt = cd.global_contrastive(leaves["img"], leaves["txt"], head.logit_scale, None, lpt, idx)  # canonical labels
-        else:
-            li, lt = F_.contrastive_over_batch(leaves["img"], leaves["txt"], head.logit_scale, lpi, lpt, idx)
-        (li + lt).backward()
-
-    def chain_ot():
-        for t in (leaves["etxt"], leaves["obj"]):
-            t.grad = None
-        loss, _ = F_.ot_alignment(leaves["etxt"], leaves["obj"], static["tnum"], static["onum"])
-        loss.backward()
-
-    def graphed(fn):
-        """Replayable CUDA graph of one chain (eager launches on a slow host would time the host)."""
-        if args.no_graph:
-            return fn
-        try:
-            s_ = torch.cuda.Stream()
-            s_.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s_):
-                fn()
-            torch.cuda.current_stream().wait_stream(s_)
-            torch.cuda.synchronize()
-            g_ = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_, capture_error_mode="thread_local"):
-                fn()
-            torch.cuda.synchronize()
-            return g_.replay
-        except Exception:
-            torch.cuda.synchronize()
-            return fn
-
+    # ---- per-chain timing for the rooflines ---------------------------------------------------
     n_seg = max(5, min(args.steps, 20))
-    ms_con = timed_loop(graphed(chain_contrastive), n_seg, 3)
-    ms_ot = timed_loop(graphed(chain_ot), n_seg, 3)
-
-    flops = algorithmic_work(w, esz, w.B, b)           # per rank: all B rows x local columns
-    ot_bytes = 2.0 * (w.M + w.N) * w.D * esz * b
-    tensor_peak = peaks["bf16_tflops"] * (1.0 if args.dtype == "bf16" else 0.5)
-    roof_gemm = {"kernel": "umma_gemm_kernel chain (ce_contrastive_fwd + ce_contrastive_bwd)", "bound": "tensor",
-                 "achieved": flops / (ms_con * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
-                 "frac": flops / (ms_con * 1e-3) / 1e12 / tensor_peak, "traffic": None, "ms": ms_con,
-                 "peak_source": peaks["source"] + (" bf16 burst" if args.dtype == "bf16" else " bf16 burst / 2 (tf32; 3 products per flop in fp32 mode)")}
-    roof_ot = {"kernel": "ot_cost_kernel + ot_ipot_kernel + ot_grad_kernel (ce_ot_fwd_bwd)", "bound": "hbm",
-               "achieved": ot_bytes / (ms_ot * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-               "frac": ot_bytes / (ms_ot * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "ms": ms_ot,
-               "peak_source": peaks["source"] + " copy bandwidth"}
-    # DRAM traffic per step of each chain, from the committed ncu --set full captures of the same
-    # workload (profiles/r01_traffic_*.json; null when there is no capture for this configuration)
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic_%s_%s.json" % (w.name, args.dtype))
-    if world == 1 and os.path.exists(tpath):
-        with open(tpath) as f:
-            tr = json.load(f)
-        roof_gemm["traffic"] = tr.get("gemm_chain_bytes_per_step")
-        roof_ot["traffic"] = tr.get("ot_chain_bytes_per_step")
-        roof_gemm["traffic_source"] = roof_ot["traffic_source"] = "profiles/" + os.path.basename(tpath)
+    ms_con, ms_ot = h.chains(n_seg)
+    roof_gemm, roof_ot = h.rooflines(ms_con, ms_ot, peaks, "%s_%s" % (w.name, args.dtype))
     dominant, secondary = (roof_gemm, roof_ot) if ms_con >= ms_ot else (roof_ot, roof_gemm)
 
-    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
+    in_bytes, flush_used = h.in_bytes, h.flush is not None
+    # ---- secondary lines (N = 1): the reference's arithmetic (fp32 mode) and the OT-dominated config ----
+    extra = None
+    if world == 1 and not args.no_secondary and args.workload == "c3" and args.dtype == "bf16":
+        extra = {}
+        del h
+        torch.cuda.empty_cache()
+        for tag, wl, dt_ in (("c3_fp32", "c3", torch.float32), ("c4_bf16", "c4", torch.bfloat16)):
+            try:
+                hh = Harness(syn.WORKLOADS[wl], dt_, 1, 0, dev, use_graph=not args.no_graph)
+                run2, _ = hh.capture(hh.step)
+                ms2 = hh.timed_loop(run2, 10, 3)
+                c2, o2 = hh.chains(5)
+                rg, ro = hh.rooflines(c2, o2, peaks)
+                extra[tag] = {"ms_per_step": ms2, "value": hh.w.B / (ms2 * 1e-3), "unit": "samples/s",
+                              "dtype": "bf16" if dt_ == torch.bfloat16 else "f32 (3xTF32 tensor-core products)",
+                              "workload": "%s: %s" % (wl, WORKLOAD_TEXT[wl]),
+                              "gemm_chain": {"ms": c2, "frac": rg["frac"], "achieved_tflops": rg["achieved"], "peak": rg["peak"]},
+                              "ot_chain": {"ms": o2, "frac": ro["frac"], "achieved_gbs": ro["achieved"], "peak": ro["peak"]},
+                              "losses": [float(x) for x in hh.losses_out.tolist()]}
+                del hh, run2
+                torch.cuda.empty_cache()
+            except Exception as e:  # pragma: no cover
+                extra[tag] = {"error": str(e)[:300]}
+                torch.cuda.synchronize()
+
+    # ---- CPU baseline (rank 0, N = 1 only): the same measurement as --impl reference ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import clip_event_oracle as orc
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        img32, txt32 = host["img"].float(), host["txt"].float()
-        e32, o32 = host["etxt"].float(), host["obj"].float()
-        rows = min(w.B, 64)
-        t0 = time.perf_counter()
-        orc.loss_head_rowblock_step(img32, txt32, ls_init, w.T, (0, rows), e32, o32, host["tnum"], host["onum"])
-        first = time.perf_counter() - t0
-        rows = int(max(16, min(w.B, rows * 4.0 / max(first, 1e-3))))      # ~4 s per timed step
-        times = []
-        for i in range(4):
-            t0 = time.perf_counter()
-            orc.loss_head_rowblock_step(img32, txt32, ls_init, w.T, (0, rows), e32, o32, host["tnum"], host["onum"])
-            times.append(time.perf_counter() - t0)
-        dt = statistics.median(times[1:])
-        cpu = {"value": rows / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "%d-image row block of the %d-image batch (scored against all %d descriptions / %d images, OT on "
-                         "the block), oracle = reference algorithm in PyTorch CPU fp32, median of 3 after 1 warm-up"
-                         % (rows, w.B, w.B * w.T, w.B)}
+        c = CpuLossHead(w)
+        times = c.time(7, 2)
+        dt_med = statistics.median(times)
+        cpu = {"value": w.B / dt_med, "unit": "samples/s", "cores": c.cores, "kind": c.kind,
+               "sample": c.describe(7, 2) + ", median", "ms_per_step_median": dt_med * 1e3,
+               "ms_per_step_mean": sum(times) / len(times) * 1e3}
 
     if rank == 0:
+        cfg = config_dict(w, world, args.dtype)
         out = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16" if args.dtype == "bf16" else "f32 (3xTF32 tensor-core products)",
-            "data": "synthetic",
-            "config": {"workload": "%s: %s" % (w.name, WORKLOAD_TEXT[w.name]), "global_batch": w.B,
-                       "per_rank_batch": b, "descriptions_per_image": w.T, "embed_dim": w.D,
-                       "ot_nodes": "%dx%d" % (w.M, w.N), "ipot_iters": 50,
-                       "parallelism": "column-sharded global negatives over %d rank(s)" % world,
-                       "l2": "inputs %.0f MB per rank %s" % (in_bytes / 1e6, "(> 126 MB L2)" if flush is None else
-                                                             "; 512 MB L2 flush write between steps"),
-                       "cuda_graph": graph is not None},
+            "data": "synthetic", "config": cfg,
+            "timing": {"cuda_graph": graphed, "per_rank_batch": w.B // world,
+                       "l2": "inputs %.0f MB per rank %s" % (in_bytes / 1e6, "(> 126 MB L2)" if not flush_used else
+                                                            "; 512 MB L2 flush write between steps"),
+                       "api": "clip_event_b200.LossHeadStep (both criteria in one call, two streams) + "
+                              "sum(loss_dict.values()).backward()"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": dominant, "roofline_secondary": secondary,
@@ -491,6 +611,10 @@ def main():
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
+        if extra is not None:
+            out["secondary"] = extra
+        if parity is not None:
+            out["dist_parity"] = parity
         print(json.dumps(out), flush=True)
     if world > 1:
         # destroy_process_group() blocks after NCCL work was replayed from CUDA graphs; everything is

@@ -110,6 +110,17 @@ def _reduce_scatter_sum(out, inp, rank, group):
         dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
 
 
+def _reduce_scatter_sums(pairs, rank, group):
+    """Several reduce-scatters as ONE NCCL launch (c10d's coalescing fast path: one ncclGroup)."""
+    if dist.get_backend(group) == "gloo":
+        for out, inp in pairs:
+            _reduce_scatter_sum(out, inp, rank, group)
+        return
+    with dist._coalescing_manager(group=group):
+        for out, inp in pairs:
+            dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
+
+
 _CANONICAL = {}
 
 
@@ -124,7 +135,7 @@ def _canonical_labels(n: int, T: int, device):
 
 class _GlobalContrastive(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img, txt, logit_scale, labels_i, labels_t, index_pos, group, compute):
+    def forward(ctx, img, txt, logit_scale, labels_i, labels_t, index_pos, group, compute, ddp_average=False):
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
         dev = img.device
@@ -154,45 +165,59 @@ class _GlobalContrastive(torch.autograd.Function):
         stats_all = stats_all.view(world, stats.numel())
         loss_i, loss_t = compute.fwd_finish(stats_all, world, state)
         ctx.saved = (img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset, state)
-        ctx.meta = (group, compute, world, rank, b, logit_scale.dtype, logit_scale.shape)
+        ctx.meta = (group, compute, world, rank, b, logit_scale.dtype, logit_scale.shape, bool(ddp_average))
         return loss_i, loss_t
 
     @staticmethod
     def backward(ctx, g_i, g_t):
         img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset, state = ctx.saved
-        group, compute, world, rank, b, ls_dtype, ls_shape = ctx.meta
+        group, compute, world, rank, b, ls_dtype, ls_shape, ddp_average = ctx.meta
         dev = txt_c.device
         def scalar(g):   # a missing upstream gradient is a zero; no launch when both are present
             if g is None:
                 return torch.zeros(1, dtype=torch.float32, device=dev)
             return g.detach().to(torch.float32).reshape(1).contiguous()
         gi, gt = scalar(g_i), scalar(g_t)
+        if ddp_average:
+            # DDP (train.py:222-225) AVERAGES parameter gradients over ranks.  The feature gradients
+            # below are d(global-mean loss)/d(local features): their per-rank contributions to an
+            # encoder parameter must be SUMMED, so they are handed to DDP multiplied by the world
+            # size; logit_scale is replicated and already carries the full (all-reduced) gradient,
+            # whose average over ranks is itself.
+            gi, gt = gi * world, gt * world
         R_total = img_all.shape[0]
         P_total = index_pos.numel() * world   # ranks hold equal shards
         dtxt, dimg_hat, dls = compute.bwd_partial(img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset,
                                                   gi, gt, R_total, P_total, state)
+        # gradient return: reduce-scatter of s G T^_local, with the dlogit_scale partials riding in the
+        # same NCCL launch (every rank contributes its partial to every chunk of a [world] vector)
         mine = torch.empty(b, dimg_hat.shape[1], dtype=torch.float32, device=dev)
-        _reduce_scatter_sum(mine, dimg_hat, rank, group)
-        dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)
+        dls_tot = torch.empty(1, dtype=torch.float32, device=dev)
+        _reduce_scatter_sums([(mine, dimg_hat), (dls_tot, dls.expand(world).contiguous())], rank, group)
+        if ddp_average:
+            dls_tot = dls_tot / world
         dimg = compute.bwd_finish(img_all[rank * b:(rank + 1) * b], mine)
-        # every rank holds the same logit_scale parameter and DDP will AVERAGE its gradient over
-        # ranks (train.py:222-225); the loss is already the global mean, so hand DDP the full
-        # gradient on every rank (the average of identical values is the value itself)
-        return dimg, dtxt, dls.reshape(ls_shape).to(ls_dtype), None, None, None, None, None
+        return dimg, dtxt, dls_tot.reshape(ls_shape).to(ls_dtype), None, None, None, None, None, None
 
 
 def global_contrastive(image_features, text_features, logit_scale, labels_per_image, labels_per_text,
-                       index_pos, group=None, compute=None):
+                       index_pos, group=None, compute=None, ddp_average=False):
     """loss_i, loss_t over the GLOBAL batch; gradients for this rank's images and descriptions.
 
     ``labels_per_image`` are global column indices (None = the canonical ``row * T``, which needs
     no exchange), ``labels_per_text`` global row indices and ``index_pos`` local column indices
     (see :func:`global_labels_for_rank`).
+
+    Gradient convention: by default every rank receives exactly its slice of the gradient of the
+    GLOBAL-mean loss (the oracle is the single-process reference on the concatenated batch).  With
+    ``ddp_average=True`` the feature gradients are multiplied by the world size, which is what an
+    encoder wrapped in DistributedDataParallel (gradient AVERAGING, train.py:222-225) needs to end up
+    with the true parameter gradient; ``logit_scale`` gets the full gradient in both modes.
     """
     if compute is None:
         compute = CudaBackend()
     return _GlobalContrastive.apply(image_features, text_features, logit_scale, labels_per_image,
-                                    labels_per_text, index_pos, group, compute)
+                                    labels_per_text, index_pos, group, compute, ddp_average)
 
 
 def sharded_alignment(entitytxt_vec, object_vec, entitytxt_num, object_num, group=None, ot_fn=None):
@@ -204,3 +229,144 @@ def sharded_alignment(entitytxt_vec, object_vec, entitytxt_num, object_num, grou
     dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     # value = global sum, gradient = local term (d total / d local nodes == d local loss / d local nodes)
     return loss + (total - loss.detach())
+
+
+# --------------------------------------------------------------------------------------------
+# the whole sharded loss head in one call: three collectives, two streams, eager gradients
+# --------------------------------------------------------------------------------------------
+def _cuda_ot_eager(etxt, obj, tnum, onum, need_grad, stream_ptr):
+    tm, kind = F_._mask_args(F_.num_mask(tnum).contiguous())
+    om, _ = F_._mask_args(F_.num_mask(onum).contiguous())
+    loss, dist_b, detxt, dobj, gbuf, ws = F_._ot_launch(etxt, obj, tm, om, kind, True, F_.IPOT_BETA, F_.IPOT_ITERS,
+                                                       F_.IPOT_K, F_.OT_LOSS_WEIGHT, need_grad, stream_ptr)
+    return loss, detxt, dobj, (gbuf, ws, dist_b)
+
+
+class _GlobalLossHeadStep(torch.autograd.Function):
+    """Sharded version of ``functional._LossHeadStep``: (loss_i, loss_t, loss_ot) over the GLOBAL batch
+    and the gradients of their sum for this rank's inputs, formed in the forward call.
+
+    Exchange steps (NCCL launches) per step: all-gather of the image embeddings, all-gather of the
+    per-rank statistics record -- the local OT loss rides in its spare slot -- and ONE coalesced
+    reduce-scatter carrying both the image-gradient return and the dlogit_scale partials.  The OT
+    chain runs on the library's side stream next to the GEMM chain and needs no exchange of its own.
+    """
+
+    @staticmethod
+    def forward(ctx, img, txt, logit_scale, etxt, obj, labels_i, labels_t, index_pos, tnum, onum, group, compute,
+                ot_eager, ddp_average):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = img.device
+        cuda = img.is_cuda
+        img_c, txt_c = img.detach().contiguous(), txt.detach().contiguous()
+        etxt_c, obj_c = etxt.detach().contiguous(), obj.detach().contiguous()
+        ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        labels_i = None if labels_i is None else labels_i.to(device=dev, dtype=torch.int64).contiguous()
+        labels_t = labels_t.to(device=dev, dtype=torch.int64).contiguous()
+        index_pos = index_pos.to(device=dev, dtype=torch.int64).contiguous()
+        b, D = img_c.shape
+        C = txt_c.shape[0]
+        need_c, need_o = any(ctx.needs_input_grad[:3]), any(ctx.needs_input_grad[3:5])
+        # OT chain first, on the side stream
+        if cuda:
+            cur, side = torch.cuda.current_stream(), F_.side_stream(dev)
+            side.wait_stream(cur)
+            loss_ot_local, detxt, dobj, keep = ot_eager(etxt_c, obj_c, tnum, onum, need_o, side.cuda_stream)
+            ot_done = torch.cuda.Event()
+            ot_done.record(side)
+        else:
+            loss_ot_local, detxt, dobj, keep = ot_eager(etxt_c, obj_c, tnum, onum, need_o, 0)
+        # 1. gather the images
+        img_all = torch.empty(world * b * D, dtype=img_c.dtype, device=dev)
+        dist.all_gather_into_tensor(img_all, img_c.view(-1), group=group)
+        img_all = img_all.view(world * b, D)
+        if labels_i is None:
+            lab_all = _canonical_labels(world * b, C // b, dev)
+        else:
+            lab_all = torch.empty(world * b, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(lab_all, labels_i, group=group)
+        # 2. local GEMM + statistics
+        col_offset = rank * C
+        stats, state = compute.fwd_partial(img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset)
+        # 3. one record per rank: [row_part (R x 4) | text-side sum, P, local OT loss, 0]
+        R = world * b
+        if cuda:
+            cur.wait_event(ot_done)
+        stats[R * 4 + 2:R * 4 + 3].copy_(loss_ot_local.reshape(1).to(torch.float32))
+        stats_all = torch.empty(world * stats.numel(), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(stats_all, stats, group=group)
+        stats_all = stats_all.view(world, stats.numel())
+        loss_i, loss_t = compute.fwd_finish(stats_all, world, state)
+        loss_ot = stats_all[:, R * 4 + 2].sum()
+        # 4. gradients of (loss_i + loss_t) for unit upstream gradients
+        dimg = dtxt = dls_tot = None
+        if need_c:
+            one = torch.ones(1, dtype=torch.float32, device=dev)
+            g = one * world if ddp_average else one
+            dtxt, dimg_hat, dls = compute.bwd_partial(img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset,
+                                                      g, g, R, index_pos.numel() * world, state)
+            mine = torch.empty(b, D, dtype=torch.float32, device=dev)
+            dls_tot = torch.empty(1, dtype=torch.float32, device=dev)
+            _reduce_scatter_sums([(mine, dimg_hat), (dls_tot, dls.expand(world).contiguous())], rank, group)
+            if ddp_average:
+                dls_tot = dls_tot / world
+            dimg = compute.bwd_finish(img_all[rank * b:(rank + 1) * b], mine)
+        if cuda:
+            cur.wait_stream(side)
+        ctx.stash = (dimg, dtxt, dls_tot, detxt, dobj, keep)
+        ctx.ls_meta = (logit_scale.dtype, logit_scale.shape)
+        ctx.set_materialize_grads(False)
+        return loss_i, loss_t, loss_ot.to(loss_i.dtype)
+
+    @staticmethod
+    def backward(ctx, g_i, g_t, g_ot):
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("clip_event_b200 sharded loss head step: backward a second time; run the step again")
+        ctx.consumed = True
+        dimg, dtxt, dls, detxt, dobj, _ = ctx.stash
+        ctx.stash = None
+        out = [None] * 14
+        if dimg is not None and (g_i is not None or g_t is not None):
+            if g_i is None or g_t is None:
+                raise RuntimeError("loss_i and loss_t must be back-propagated together on the fused step")
+            ls_dtype, ls_shape = ctx.ls_meta
+            if dimg.is_cuda:   # scale launches that return on the device when the upstream gradient is 1
+                lib = L.load()
+                gi = g_i.detach().to(torch.float32).reshape(1).contiguous()
+                gt = g_t.detach().to(torch.float32).reshape(1).contiguous()
+                for t in (dimg, dtxt, dls):
+                    L.check(lib.ce_scale_inplace_same(t.data_ptr(), t.numel(), L.dtype_code(t.dtype), gi.data_ptr(),
+                                                      gt.data_ptr(), L.stream_ptr()), "sharded loss head step backward")
+            else:
+                gf, gtf = g_i.detach().float(), g_t.detach().float()
+                g = torch.where(gf == gtf, gf, torch.full_like(gf, float("nan")))
+                dimg, dtxt, dls = (dimg.float() * g).to(dimg.dtype), (dtxt.float() * g).to(dtxt.dtype), dls * g
+            out[0], out[1], out[2] = dimg, dtxt, dls.reshape(ls_shape).to(ls_dtype)
+        if detxt is not None and g_ot is not None:
+            if detxt.is_cuda:
+                lib = L.load()
+                g = g_ot.detach().to(torch.float32).reshape(1).contiguous()
+                for t in (detxt, dobj):
+                    tc = t if t.is_contiguous() else t.contiguous()
+                    L.check(lib.ce_scale_inplace(tc.data_ptr(), 1, tc.numel(), tc.numel(), L.dtype_code(tc.dtype),
+                                                 g.data_ptr(), L.stream_ptr()), "sharded loss head step backward")
+            else:
+                g = g_ot.detach().float()
+                detxt, dobj = (detxt.float() * g).to(detxt.dtype), (dobj.float() * g).to(dobj.dtype)
+            out[3], out[4] = detxt, dobj
+        return tuple(out)
+
+
+def global_loss_head_step(image_features, text_features, logit_scale, labels_per_image, labels_per_text, index_pos,
+                          entitytxt_vec, object_vec, entitytxt_num, object_num, group=None, compute=None,
+                          ot_eager=None, ddp_average=False):
+    """(loss_i, loss_t, loss_ot) over the global batch in one call (labels as in :func:`global_contrastive`).
+    loss_ot is the GLOBAL sum (replicated); its gradient w.r.t. this rank's nodes is the local term, which is
+    what the reference's per-rank loss under DDP averaging corresponds to (no scaling in either mode)."""
+    if compute is None:
+        compute = CudaBackend()
+    if ot_eager is None:
+        ot_eager = _cuda_ot_eager
+    return _GlobalLossHeadStep.apply(image_features, text_features, logit_scale, entitytxt_vec, object_vec,
+                                     labels_per_image, labels_per_text, index_pos, entitytxt_num, object_num,
+                                     group, compute, ot_eager, ddp_average)

@@ -1,6 +1,7 @@
 """Autograd bindings of the CUDA loss-head kernels (thin: argument checks, buffers, ctypes calls)."""
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -19,6 +20,14 @@ def _i64(t: torch.Tensor, device) -> torch.Tensor:
 
 def _scalar_f32(t: torch.Tensor, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
+
+
+def _debug_check_finite(losses: torch.Tensor, what: str) -> None:
+    """Index errors come back from the kernels as NaN losses (no host synchronisation on the hot
+    path).  With CE_CHECK_INPUTS=1 the losses are read back here and a RuntimeError names the cause,
+    which is what the reference's IndexError would have said."""
+    if os.environ.get("CE_CHECK_INPUTS") == "1" and bool(torch.isnan(losses).any()):
+        raise RuntimeError("clip_event_b200 " + what)
 
 
 # --------------------------------------------------------------------------------------------
@@ -51,6 +60,13 @@ class _ContrastiveOverBatch(torch.autograd.Function):
         labels_t, index_pos = _i64(labels_t, dev), _i64(index_pos, dev)
         B, D = img_c.shape
         BT, P = txt_c.shape[0], index_pos.numel()
+        # the reference index_selects labels_per_text with index_pos (model_clip.py:656): a shorter
+        # vector is an IndexError there, and an out-of-bounds device read here -- refuse it
+        if labels_t.numel() != BT:
+            raise RuntimeError("labels_per_text must have one entry per description (%d), got %d"
+                               % (BT, labels_t.numel()))
+        if P < 1:
+            raise RuntimeError("index_pos is empty: the text-side loss has no rows (model_clip.py:655-659)")
         if mode == L.CE_IMG_BCE_INSTANCE:
             labels_i = labels_i.to(device=dev, dtype=torch.float32).contiguous()
             if B == 0 or BT % B or labels_i.numel() != BT:
@@ -68,6 +84,8 @@ class _ContrastiveOverBatch(torch.autograd.Function):
         L.check(lib.ce_contrastive_fwd(L.ptr(img_c), L.ptr(txt_c), L.ptr(ls), L.ptr(labels_i), L.ptr(labels_t),
                                        L.ptr(index_pos), B, BT, P, D, mode, dt, out.data_ptr(), out.data_ptr() + 4,
                                        ws.data_ptr(), nbytes, L.stream_ptr()), "contrastive forward")
+        _debug_check_finite(out, "contrastive forward: an index in labels_per_image / labels_per_text / index_pos "
+                                 "is out of range or index_pos lists a description twice")
         ctx.save_for_backward(img_c, txt_c, ls, labels_i, labels_t, index_pos, ws)
         ctx.dims = (B, BT, P, D, dt, mode)
         ctx.ls_dtype = logit_scale.dtype
@@ -109,6 +127,65 @@ def contrastive_over_instance(image_features, text_features, logit_scale, labels
                                        labels_per_text, index_pos, loss + "_instance")
 
 
+class _DenseCrossEntropy(torch.autograd.Function):
+    """mean cross-entropy (or BCE with logits) over the rows of a MATERIALISED logits matrix,
+    optionally over ``logits.index_select(0, row_index)`` -- model_clip.py:648-659 on plain tensors."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, row_index, labels_by_row, kind):
+        L.require_cuda(logits, labels)
+        if logits.dim() != 2:
+            raise RuntimeError("expected a [rows, classes] logits matrix")
+        dt = L.dtype_code(logits.dtype)
+        dev = logits.device
+        lg = logits.detach().contiguous()
+        rows, cols = lg.shape
+        if kind == 1:
+            lab = labels.to(device=dev, dtype=torch.float32).contiguous()
+            if lab.shape != lg.shape:
+                raise RuntimeError("'bce' labels_per_image must have the shape of logits_per_image")
+        else:
+            lab = _i64(labels, dev)
+        ri = None if row_index is None else _i64(row_index, dev)
+        n = rows if ri is None else ri.numel()
+        if kind == 0 and lab.numel() != (rows if (labels_by_row or ri is None) else n):
+            raise RuntimeError("labels must have one entry per logits row")
+        if n < 1:
+            raise RuntimeError("no rows to average over")
+        lib = L.load()
+        nbytes = lib.ce_dense_ce_workspace_bytes(n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        L.check(lib.ce_dense_ce_fwd(lg.data_ptr(), cols, rows, cols, L.ptr(ri), n, lab.data_ptr(), int(labels_by_row),
+                                    int(kind), dt, loss.data_ptr(), ws.data_ptr(), nbytes, L.stream_ptr()), "dense CE forward")
+        _debug_check_finite(loss, "dense cross-entropy: a label or index_pos entry is out of range")
+        ctx.save_for_backward(lg, lab, ri if ri is not None else torch.empty(0, device=dev), ws)
+        ctx.meta = (rows, cols, n, ri is not None, int(labels_by_row), int(kind), dt)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, lab, ri, ws = ctx.saved_tensors
+        rows, cols, n, has_ri, by_row, kind, dt = ctx.meta
+        gg = _scalar_f32(g, lg.device)
+        d = torch.empty(rows, cols, dtype=torch.float32, device=lg.device)
+        L.check(L.load().ce_dense_ce_bwd(lg.data_ptr(), cols, rows, cols, ri.data_ptr() if has_ri else 0, n, lab.data_ptr(),
+                                         by_row, kind, dt, gg.data_ptr(), d.data_ptr(), cols, ws.data_ptr(), L.stream_ptr()),
+                "dense CE backward")
+        return d.to(lg.dtype), None, None, None, None
+
+
+def dense_contrastive(logits_per_image, logits_per_text, labels_per_image, labels_per_text, index_pos, loss="ce"):
+    """``CriterionContrastive.forward`` on materialised logits (any producer): loss_i over the rows of
+    ``logits_per_image`` ('ce' or 'bce'), loss_t over ``logits_per_text[index_pos]`` with
+    ``labels_per_text[index_pos]`` (model_clip.py:648-659)."""
+    if loss not in ("ce", "bce"):
+        raise RuntimeError("Invalid constrastive_loss '{}'. ".format(loss))
+    loss_i = _DenseCrossEntropy.apply(logits_per_image, labels_per_image, None, False, 1 if loss == "bce" else 0)
+    loss_t = _DenseCrossEntropy.apply(logits_per_text, labels_per_text, index_pos, True, 0)
+    return loss_i, loss_t
+
+
 def similarity_logits(a: torch.Tensor, b: torch.Tensor, logit_scale: torch.Tensor) -> torch.Tensor:
     """Dense ``exp(logit_scale) * normalize(a) @ normalize(b).T`` (fp32), no autograd."""
     L.require_cuda(a, b, logit_scale)
@@ -140,6 +217,12 @@ def _mask_args(mask: torch.Tensor):
     if mask.dtype == torch.uint8:
         return mask, L.CE_MASK_PAD_U8
     return mask.to(torch.int64), L.CE_MASK_NUM_I64
+
+
+def num_mask(mask: torch.Tensor) -> torch.Tensor:
+    """``*_num`` arrays of CriterionAlignment (model_clip.py:679-690): nonzero = valid node, whatever
+    the dtype (the reference applies ``mask2pad(x) = (x == 0)``); the kernels read them as int64."""
+    return mask if mask.dtype == torch.int64 else mask.to(torch.int64)
 
 
 class _OtAlignment(torch.autograd.Function):
@@ -233,3 +316,160 @@ def ot_alignment(txt_nodes, object_vec, txt_mask, object_mask, drop_slot0=True, 
                  iters=IPOT_ITERS, k=IPOT_K, loss_scale=OT_LOSS_WEIGHT):
     """(loss_scale * sum_b dist[b], dist[B]) for text nodes vs image nodes (slot 0 dropped if asked)."""
     return _OtAlignment.apply(txt_nodes, object_vec, txt_mask, object_mask, drop_slot0, beta, iters, k, loss_scale)
+
+
+# --------------------------------------------------------------------------------------------
+# one call for engine.py:48-67,88: both criteria, two streams, gradients formed with the losses
+# --------------------------------------------------------------------------------------------
+_SIDE_STREAMS = {}
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+    """The library's second stream on ``device`` (the OT chain runs there, next to the GEMM chain)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
+
+
+def _ot_launch(txt_c, obj_c, tm, om, kind, drop_slot0, beta, iters, k, loss_scale, need_grad, stream_ptr):
+    """Allocate the OT buffers (on the CURRENT stream's pool) and enqueue ce_ot_fwd_bwd on ``stream_ptr``."""
+    B, M, D = txt_c.shape
+    slot = 1 if drop_slot0 else 0
+    N = obj_c.shape[1] - slot
+    esz, msz, dev = txt_c.element_size(), om.element_size(), txt_c.device
+    lib = L.load()
+    nbytes = lib.ce_ot_workspace_bytes(B, M, N, D)
+    if nbytes == 0:
+        raise RuntimeError("clip_event_b200 OT: unsupported node counts M=%d N=%d" % (M, N))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dist = torch.empty(B, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    if need_grad:
+        n_t = txt_c.numel()
+        n_t_pad = (n_t + 7) // 8 * 8
+        gbuf = torch.empty(n_t_pad + obj_c.numel(), dtype=txt_c.dtype, device=dev)
+        if n_t_pad != n_t:
+            gbuf[n_t:n_t_pad].zero_()
+        dtxt, dobj = gbuf[:n_t].view_as(txt_c), gbuf[n_t_pad:].view_as(obj_c)
+    else:
+        gbuf = dtxt = dobj = None
+    L.check(lib.ce_ot_fwd_bwd(
+        txt_c.data_ptr(), M * D, obj_c.data_ptr() + slot * D * esz, (N + slot) * D,
+        tm.data_ptr(), M, om.data_ptr() + slot * msz, N + slot, kind, B, M, N, D, L.dtype_code(txt_c.dtype),
+        float(beta), int(iters), int(k), float(loss_scale), dist.data_ptr(), loss.data_ptr(),
+        L.ptr(dtxt), 0 if dobj is None else dobj.data_ptr() + slot * D * esz,
+        0 if (dobj is None or not slot) else dobj.data_ptr(), ws.data_ptr(), nbytes, stream_ptr), "OT forward")
+    return loss, dist, dtxt, dobj, gbuf, ws
+
+
+class _LossHeadStep(torch.autograd.Function):
+    """(image_features, text_features, logit_scale, entitytxt_vec, object_vec) -> (loss_i, loss_t, loss_ot).
+
+    engine.py:48-67 computes the two criteria back to back and line 88 back-propagates their plain
+    sum.  Neither gradient depends on the upstream gradient except as a scale, so this call forms
+    losses AND gradients at once: the similarity/InfoNCE chain (tensor-core bound) on the current
+    stream, the OT chain (HBM/ALU bound) on the library's side stream, joined before it returns.
+    ``backward`` is two scale launches that return immediately on the device when the upstream
+    gradients are 1.  loss_i and loss_t must receive the SAME upstream gradient (they do under
+    ``sum(loss_dict.values())``); anything else turns the contrastive gradients into NaN rather than
+    passing silently -- use the separate criteria for weighted sums.
+    """
+
+    @staticmethod
+    def forward(ctx, img, txt, logit_scale, etxt, obj, labels_i, labels_t, index_pos, tnum, onum, image_loss):
+        L.require_cuda(img, txt, logit_scale, etxt, obj, tnum, onum)
+        if img.dtype != txt.dtype or etxt.dtype != obj.dtype:
+            raise RuntimeError("features must share a dtype")
+        dev = img.device
+        dt = L.dtype_code(img.dtype)
+        img_c, txt_c = img.detach().contiguous(), txt.detach().contiguous()
+        etxt_c, obj_c = etxt.detach().contiguous(), obj.detach().contiguous()
+        ls = _scalar_f32(logit_scale, dev)
+        mode = IMAGE_LOSS[image_loss]
+        labels_t, index_pos = _i64(labels_t, dev), _i64(index_pos, dev)
+        labels_i = labels_i.to(device=dev, dtype=torch.float32).contiguous() if mode == L.CE_IMG_BCE_INSTANCE else _i64(labels_i, dev)
+        B, D = img_c.shape
+        BT, P = txt_c.shape[0], index_pos.numel()
+        if labels_t.numel() != BT or P < 1:
+            raise RuntimeError("labels_per_text must have one entry per description and index_pos at least one")
+        tm, kind_t = _mask_args(num_mask(tnum).contiguous())
+        om, kind_o = _mask_args(num_mask(onum).contiguous())
+        need_c = any(ctx.needs_input_grad[:3])
+        need_o = any(ctx.needs_input_grad[3:5])
+        lib = L.load()
+        cur = torch.cuda.current_stream()
+        side = side_stream(dev)
+        # OT chain on the side stream (buffers come from the current stream's pool; the join below orders every later use)
+        side.wait_stream(cur)
+        loss_ot, dist, detxt, dobj, gbuf, ws_ot = _ot_launch(etxt_c, obj_c, tm, om, kind_t, True, IPOT_BETA, IPOT_ITERS,
+                                                             IPOT_K, OT_LOSS_WEIGHT, need_o, side.cuda_stream)
+        # similarity + InfoNCE chain on the current stream
+        nbytes = lib.ce_contrastive_workspace_bytes(B, BT, P, D, dt)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        sp = cur.cuda_stream
+        L.check(lib.ce_contrastive_fwd(L.ptr(img_c), L.ptr(txt_c), L.ptr(ls), L.ptr(labels_i), L.ptr(labels_t),
+                                       L.ptr(index_pos), B, BT, P, D, mode, dt, out.data_ptr(), out.data_ptr() + 4,
+                                       ws.data_ptr(), nbytes, sp), "contrastive forward")
+        if need_c:
+            one = torch.ones(1, dtype=torch.float32, device=dev)
+            # dimg | dtxt in one allocation (one scale launch in the backward), dls apart (fp32)
+            n_i = img_c.numel()
+            n_i_pad = (n_i + 7) // 8 * 8
+            cbuf = torch.empty(n_i_pad + txt_c.numel(), dtype=img_c.dtype, device=dev)
+            if n_i_pad != n_i:
+                cbuf[n_i:n_i_pad].zero_()
+            dimg, dtxt = cbuf[:n_i].view_as(img_c), cbuf[n_i_pad:].view_as(txt_c)
+            dls = torch.empty(1, dtype=torch.float32, device=dev)
+            L.check(lib.ce_contrastive_bwd(L.ptr(img_c), L.ptr(txt_c), L.ptr(ls), L.ptr(labels_i), L.ptr(labels_t),
+                                           L.ptr(index_pos), B, BT, P, D, mode, dt, L.ptr(one), L.ptr(one), L.ptr(dimg),
+                                           L.ptr(dtxt), L.ptr(dls), ws.data_ptr(), nbytes, sp), "contrastive backward")
+        else:
+            cbuf = dimg = dtxt = dls = None
+        cur.wait_stream(side)           # join: everything below and after sees both chains
+        out[2:3].copy_(loss_ot)
+        ctx.stash = (cbuf, dimg, dtxt, dls, gbuf, detxt, dobj)
+        ctx.ls_meta = (logit_scale.dtype, logit_scale.shape)
+        ctx.set_materialize_grads(False)
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_i, g_t, g_ot):
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("clip_event_b200 loss head step: backward a second time; run the step again "
+                               "(retain_graph is not supported on this path)")
+        cbuf, dimg, dtxt, dls, gbuf, detxt, dobj = ctx.stash
+        if cbuf is None and gbuf is None:
+            return (None,) * 11
+        ctx.consumed = True
+        ctx.stash = (None,) * 7
+        lib = L.load()
+        out = [None] * 11
+        if cbuf is not None and (g_i is not None or g_t is not None):
+            if g_i is None or g_t is None:
+                raise RuntimeError("clip_event_b200 loss head step: loss_i and loss_t must be back-propagated together "
+                                   "(use CriterionContrastive for a single-sided or weighted loss)")
+            dev = cbuf.device
+            gi, gt = _scalar_f32(g_i, dev), _scalar_f32(g_t, dev)
+            dtc = L.dtype_code(cbuf.dtype)
+            L.check(lib.ce_scale_inplace_same(cbuf.data_ptr(), cbuf.numel(), dtc, gi.data_ptr(), gt.data_ptr(), L.stream_ptr()),
+                    "loss head step backward")
+            L.check(lib.ce_scale_inplace_same(dls.data_ptr(), 1, L.CE_F32, gi.data_ptr(), gt.data_ptr(), L.stream_ptr()),
+                    "loss head step backward")
+            ls_dtype, ls_shape = ctx.ls_meta
+            out[0], out[1], out[2] = dimg, dtxt, dls.reshape(ls_shape).to(ls_dtype)
+        if gbuf is not None and g_ot is not None:
+            g = _scalar_f32(g_ot, gbuf.device)
+            L.check(lib.ce_scale_inplace(gbuf.data_ptr(), 1, gbuf.numel(), gbuf.numel(), L.dtype_code(gbuf.dtype),
+                                         g.data_ptr(), L.stream_ptr()), "loss head step backward")
+            out[3], out[4] = detxt, dobj
+        return tuple(out)
+
+
+def loss_head_step(image_features, text_features, logit_scale, labels_per_image, labels_per_text, index_pos,
+                   entitytxt_vec, object_vec, entitytxt_num, object_num, image_loss="ce_overbatch"):
+    """(loss_i, loss_t, loss_ot) of the whole loss head in one call; see :class:`_LossHeadStep`."""
+    return _LossHeadStep.apply(image_features, text_features, logit_scale, entitytxt_vec, object_vec,
+                               labels_per_image, labels_per_text, index_pos, entitytxt_num, object_num, image_loss)

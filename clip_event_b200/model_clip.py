@@ -105,23 +105,65 @@ class ClipEventHead(nn.Module):
         return image_features, text_features
 
 
-class CriterionContrastive(nn.Module):
-    """model_clip.py:620-662."""
+def _localise_labels(labels_per_image, labels_per_text, b, cols_local, group):
+    """The reference's collate_fn numbers rows and columns within ONE rank's batch
+    (dataset_voa.py:617-663).  The sharded kernels want labels_per_image as GLOBAL column indices and
+    labels_per_text as GLOBAL row indices: shift by this rank's offsets."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    # a training loop hands over the same label tensors every step: shift them once
+    key = (labels_per_image.data_ptr(), labels_per_text.data_ptr(), labels_per_image._version, labels_per_text._version,
+           rank, b, cols_local)
+    hit = _LOCALISED.get(key)
+    if hit is None:
+        if len(_LOCALISED) > 16:
+            _LOCALISED.clear()
+        hit = _LOCALISED[key] = (labels_per_image + rank * cols_local, labels_per_text + rank * b,
+                                 labels_per_image, labels_per_text)   # keep the sources alive: the key is their address
+    return hit[0], hit[1]
 
-    def __init__(self, constrastive_loss):
+
+_LOCALISED = {}
+
+
+class CriterionContrastive(nn.Module):
+    """model_clip.py:620-662.
+
+    ``forward`` takes what ``ClipEventHead.forward`` returns (LazyLogits -> fused tcgen05 GEMM +
+    cross-entropy, the logits are never written to HBM) or, like the reference, any materialised
+    logits tensors (memory-bound row kernels, ``functional.dense_contrastive``).
+
+    ``group`` (a torch.distributed process group, or ``True`` for the default group) turns on global
+    negatives: image embeddings are all-gathered so that every rank scores against the global batch
+    and the image gradient is reduce-scattered back (the reference's own
+    ``utils.gather_tensors``, utils.py:192-206, is dead code).  Labels stay the per-rank ones the
+    reference's collate_fn builds.  ``ddp_average`` (default True with a group): feature gradients are
+    scaled for an encoder wrapped in DistributedDataParallel -- see ``distributed.global_contrastive``.
+    """
+
+    def __init__(self, constrastive_loss, group=None, ddp_average=True, compute=None):
         super().__init__()
         if constrastive_loss not in ("ce", "bce", "kl"):
             raise RuntimeError("Invalid constrastive_loss '{}'. ".format(constrastive_loss))
         self.constrastive_loss = constrastive_loss
+        self.group = group
+        self.ddp_average = ddp_average
+        self._compute = compute     # tests inject a CPU stand-in for the kernels
+
+    def _pg(self):
+        return None if self.group is True else self.group
 
     def forward(self, logits_per_image, logits_per_text, labels_per_image=None, labels_per_text=None,
                 index_pos=None, constrastive_overbatch=True):
-        if not isinstance(logits_per_image, LazyLogits) or not isinstance(logits_per_text, LazyLogits):
-            raise RuntimeError("clip_event_b200.CriterionContrastive fuses the similarity GEMM with the "
-                               "cross-entropy: pass the LazyLogits returned by ClipEventHead.forward")
-        img, txt, ls = logits_per_image.rows, logits_per_image.cols, logits_per_image.logit_scale
-        B = img.shape[0]
-        dev = img.device
+        lazy = isinstance(logits_per_image, LazyLogits) and isinstance(logits_per_text, LazyLogits)
+        if not lazy and (isinstance(logits_per_image, LazyLogits) or isinstance(logits_per_text, LazyLogits)):
+            logits_per_image = logits_per_image.materialize() if isinstance(logits_per_image, LazyLogits) else logits_per_image
+            logits_per_text = logits_per_text.materialize() if isinstance(logits_per_text, LazyLogits) else logits_per_text
+        if lazy:
+            img, txt, ls = logits_per_image.rows, logits_per_image.cols, logits_per_image.logit_scale
+            B, dev, out_dtype = img.shape[0], img.device, img.dtype
+        else:
+            B, dev, out_dtype = logits_per_image.shape[0], logits_per_image.device, logits_per_image.dtype
         if labels_per_image is None:
             labels_per_image = torch.arange(B, device=dev)     # model_clip.py:635-637
         if labels_per_text is None:
@@ -132,6 +174,12 @@ class CriterionContrastive(nn.Module):
             # the reference's 'kl' path is unusable: its collate_fn calls torch.zeros() with no shape
             # (dataset_voa.py:642) and feeds raw logits to KLDivLoss (model_clip.py:628-629)
             raise RuntimeError("constrastive_loss 'kl' is broken in the reference and not provided")
+        if not lazy:
+            if self.group is not None:
+                raise RuntimeError("global negatives need the features: pass the LazyLogits of ClipEventHead.forward")
+            loss_i, loss_t = F_.dense_contrastive(logits_per_image, logits_per_text, labels_per_image, labels_per_text,
+                                                  index_pos, self.constrastive_loss)
+            return {"loss_i": loss_i.to(out_dtype), "loss_t": loss_t.to(out_dtype)}
         if logits_per_image.per_instance != (not constrastive_overbatch):
             raise RuntimeError("constrastive_overbatch=%s does not match the logits the head produced "
                                "(ClipEventHead.set_hyps)" % constrastive_overbatch)
@@ -139,22 +187,81 @@ class CriterionContrastive(nn.Module):
             if self.constrastive_loss != "ce":
                 # dataset_voa.py:628-631: "Set constrastive_overbatch=false for constrative_loss=='bce'."
                 raise RuntimeError("Set constrastive_overbatch=false for constrative_loss=='bce'.")
-            loss_i, loss_t = F_.contrastive_over_batch(img, txt, ls, labels_per_image, labels_per_text, index_pos)
+            if self.group is not None:
+                from . import distributed as cd
+                lpi, lpt = _localise_labels(labels_per_image.to(dev), labels_per_text.to(dev), B, txt.shape[0], self._pg())
+                loss_i, loss_t = cd.global_contrastive(img, txt, ls, lpi, lpt, index_pos, group=self._pg(),
+                                                       compute=self._compute, ddp_average=self.ddp_average)
+            else:
+                loss_i, loss_t = F_.contrastive_over_batch(img, txt, ls, labels_per_image, labels_per_text, index_pos)
         else:
+            if self.group is not None:
+                raise RuntimeError("global negatives are defined for constrastive_overbatch=True")
             loss_i, loss_t = F_.contrastive_over_instance(img, txt, ls, labels_per_image, labels_per_text,
                                                           index_pos, self.constrastive_loss)
-        return {"loss_i": loss_i.to(img.dtype), "loss_t": loss_t.to(img.dtype)}
+        return {"loss_i": loss_i.to(out_dtype), "loss_t": loss_t.to(out_dtype)}
 
 
 class CriterionAlignment(nn.Module):
-    """model_clip.py:664-715: OT distance between text nodes and image nodes, summed, times 0.01."""
+    """model_clip.py:664-715: OT distance between text nodes and image nodes, summed, times 0.01.
 
-    def __init__(self):
+    With ``group`` the returned loss is the sum over the GLOBAL batch (one scalar all-reduce); the
+    gradient w.r.t. this rank's nodes is the local term, as in the reference under DDP."""
+
+    def __init__(self, group=None):
         super().__init__()
+        self.group = group
 
     def mask2pad(self, x_mask):
         return x_mask == 0
 
     def forward(self, entitytxt_vec, object_vec, entitytxt_num, object_num):
-        loss, _ = F_.ot_alignment(entitytxt_vec, object_vec, entitytxt_num, object_num, drop_slot0=True)
+        # *_num semantics whatever the dtype: nonzero = valid node (the reference applies mask2pad, :688-690)
+        tnum, onum = F_.num_mask(entitytxt_num), F_.num_mask(object_num)
+        if self.group is not None:
+            from . import distributed as cd
+            loss = cd.sharded_alignment(entitytxt_vec, object_vec, tnum, onum, group=None if self.group is True else self.group)
+        else:
+            loss, _ = F_.ot_alignment(entitytxt_vec, object_vec, tnum, onum, drop_slot0=True)
         return {"loss_ot": loss.to(entitytxt_vec.dtype)}
+
+
+class LossHeadStep(nn.Module):
+    """engine.py:48-67 in ONE call: both criteria of the loss head, ready for ``sum(...).backward()``.
+
+        step = LossHeadStep(head)                       # head: ClipEventHead (owns logit_scale)
+        loss_dict = step(image_features, text_features, labels_per_image, labels_per_text, index_pos,
+                         entitytxt_vec, object_vec, entitytxt_num, object_num)
+        losses = sum(loss_dict.values()); losses.backward()          # engine.py:67,88 unchanged
+
+    Same numbers as ``CriterionContrastive('ce')`` + ``CriterionAlignment()`` called one after the
+    other; what the single call buys is overlap: the tensor-core chain and the OT chain run on two
+    streams, and their gradients are formed together with the losses (``backward`` only scales).
+    With ``group`` the batch is sharded over the ranks with global negatives (three NCCL launches
+    per step, see ``distributed.global_loss_head_step``); labels are the per-rank ones.
+    """
+
+    def __init__(self, head: ClipEventHead, group=None, ddp_average=True):
+        super().__init__()
+        self.head = head
+        self.group = group
+        self.ddp_average = ddp_average
+
+    def forward(self, image_features, text_features, labels_per_image, labels_per_text, index_pos,
+                entitytxt_vec, object_vec, entitytxt_num, object_num):
+        if not self.head.constrastive_overbatch:
+            raise RuntimeError("LossHeadStep covers constrastive_overbatch=True; use the criteria for the over-instance modes")
+        ls = self.head.logit_scale
+        if self.group is not None:
+            from . import distributed as cd
+            pg = None if self.group is True else self.group
+            B = image_features.shape[0]
+            lpi, lpt = _localise_labels(labels_per_image, labels_per_text, B, text_features.shape[0], pg)
+            li, lt, lo = cd.global_loss_head_step(image_features, text_features, ls, lpi, lpt, index_pos, entitytxt_vec,
+                                                  object_vec, entitytxt_num, object_num, group=pg,
+                                                  ddp_average=self.ddp_average)
+        else:
+            li, lt, lo = F_.loss_head_step(image_features, text_features, ls, labels_per_image, labels_per_text,
+                                           index_pos, entitytxt_vec, object_vec, entitytxt_num, object_num)
+        dt = image_features.dtype
+        return {"loss_i": li.to(dt), "loss_t": lt.to(dt), "loss_ot": lo.to(entitytxt_vec.dtype)}

@@ -12,7 +12,9 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory,
  *     including workspaces (sizes from the *_workspace_bytes queries); the library never allocates
- *     device memory and keeps no state besides a thread-local error string;
+ *     device memory; its only state is a thread-local error string, the launch counter behind
+ *     ce_debug_launch_count() and a few debug switches read once from the environment
+ *     (CE_GEMM_PAIR, CE_OT_FUSED, CE_OT_POLL, CE_OT_TRACE_PTR -- tuning aids, not configuration);
  *   - tensors are row-major and contiguous unless a stride argument says otherwise; embedding
  *     pointers must be 16-byte aligned and D a multiple of 8;
  *   - dtype: CE_F32 = fp32 in / fp32 out, tensor-core products as 3xTF32 (fp32-level accuracy);
@@ -78,6 +80,12 @@ int ce_device_check(void);
  *                are rows [row_offset, row_offset + b) of `img`, against their own T descriptions
  *   labels_t     [C]      int64 GLOBAL row index each local description belongs to (labels_per_text)
  *   index_pos    [P]      int64 LOCAL column indices used for the text-side loss  (index_pos)
+ *
+ * Index errors (labels_per_image outside [0, B*T) on one GPU / negative when sharded, index_pos
+ * outside [0, C), labels_per_text[index_pos] outside [0, R), a description listed twice in
+ * index_pos) raise an IndexError in the reference.  Here the indices are clamped -- nothing is read
+ * or written out of bounds -- and BOTH LOSSES COME BACK AS NaN, which engine.py:79-82 turns into
+ * "Loss is nan, stopping training".
  * ------------------------------------------------------------------------------------------ */
 size_t ce_contrastive_workspace_bytes(int R, int C, int P, int D, int dtype);
 
@@ -186,6 +194,34 @@ int ce_ot_trace(const float* x, int B, int n, float* out, ce_stream_t stream);
  * returns immediately on the device when *g == 1. */
 int ce_scale_inplace(void* x, int64_t rows, int64_t row_len, int64_t row_stride, int dtype,
                      const float* g, ce_stream_t stream);
+
+/* Same, for gradients that were formed assuming EQUAL upstream gradients of two losses (the fused
+ * step of the loss head under `sum(loss_dict.values()).backward()`, engine.py:67,88): x[i] *= *g, and
+ * every element becomes NaN if *g_same != *g. */
+int ce_scale_inplace_same(void* x, int64_t n, int dtype, const float* g, const float* g_same,
+                          ce_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CriterionContrastive on MATERIALISED logits (model_clip.py:633-662): the reference's criterion
+ * accepts any logits tensors.  Memory-bound row kernels (one CTA per row, 16-byte loads):
+ *   loss = mean_p ( LSE(logits[r_p, :]) - logits[r_p, label_p] ),  r_p = row_index ? row_index[p] : p
+ *          -- nn.CrossEntropyLoss()(logits.index_select(0, row_index), labels...)   (kind 0)
+ *   loss = mean over all elements of softplus(l) - y l  -- nn.BCEWithLogitsLoss()       (kind 1,
+ *          labels fp32 [n, cols])
+ *   labels: int64, indexed by p (labels_by_row = 0) or by r_p (labels_by_row = 1, i.e.
+ *           labels_per_text.index_select(0, index_pos)); out-of-range indices give a NaN loss.
+ * Backward: dlogits [rows_total, ldd] fp32 = g/n (softmax - onehot) on the selected rows (rows named
+ * twice accumulate; with a row_index the matrix is zero-filled first).  `workspace` carries the row
+ * LSEs from the forward.
+ * ------------------------------------------------------------------------------------------ */
+size_t ce_dense_ce_workspace_bytes(int n);
+int ce_dense_ce_fwd(const void* logits, int64_t ld, int64_t rows_total, int cols,
+                    const int64_t* row_index, int n, const void* labels, int labels_by_row, int kind,
+                    int dtype, float* loss, void* workspace, size_t workspace_bytes, ce_stream_t stream);
+int ce_dense_ce_bwd(const void* logits, int64_t ld, int64_t rows_total, int cols,
+                    const int64_t* row_index, int n, const void* labels, int labels_by_row, int kind,
+                    int dtype, const float* g, float* dlogits, int64_t ldd, const void* workspace,
+                    ce_stream_t stream);
 
 /* Number of kernels this library has launched in this process (for benchmark bookkeeping). */
 unsigned long long ce_debug_launch_count(void);

@@ -1,0 +1,250 @@
+"""Round-2 parity cases (GPU): solver iteration counts / beta, the big-plan solver, production
+temperatures, input validation, the dense-logits criterion, mask semantics, the one-call step and
+the shared-memory-resident OT kernel.  Same tolerances as tests/test_gpu_parity.py."""
+import math
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import rel_err
+import clip_event_b200 as ce
+from clip_event_b200 import functional as F_
+from clip_event_b200 import synthetic as syn
+from oracle import clip_event_oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+F32_LOSS_RTOL, F32_LOSS_ATOL, F32_GRAD = 1e-5, 2e-6, 2e-5
+BF16_LOSS_RTOL, BF16_GRAD = 2e-3, 1e-2
+
+
+def close(a, b, rtol, atol=0.0):
+    return abs(float(a) - float(b)) <= rtol * abs(float(b)) + atol
+
+
+# ------------------------------------------------------------------------------------------
+# IPOT with other iteration counts and beta (BASELINE config c5: iterations 10-100); the factorised
+# plan is refolded every few iterations, so 100 iterations is where a range problem would show
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,D", [(16, 50, 512), (32, 257, 768), (64, 577, 768)])
+@pytest.mark.parametrize("iters", [10, 25, 100])
+@pytest.mark.parametrize("beta", [0.3, 0.5])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ot_iterations_and_beta(M, N, D, iters, beta, dtype):
+    B = 6
+    txt, obj, tnum, onum = syn.ot_inputs(B, M, N, D, 17, "ragged", dtype=dtype)
+    tp, ip = tnum == 0, onum[:, 1:] == 0
+    d_ref, dx_ref, dy_ref = orc.ot_closed_form_grads(txt.double(), obj.double()[:, 1:], tp, ip,
+                                                     torch.ones(B, dtype=torch.float64), beta=beta, iteration=iters)
+    tg, og = txt.cuda().requires_grad_(True), obj[:, 1:].contiguous().cuda().requires_grad_(True)
+    dist = ce.optimal_transport_dist(tg, og, tp.cuda(), ip.cuda(), beta=beta, iteration=iters)     # model_ot.py:66-68
+    dist.float().sum().backward()
+    torch.cuda.synchronize()
+    if dtype == torch.float32:
+        assert rel_err(dist, d_ref) < F32_LOSS_RTOL
+        assert rel_err(tg.grad, dx_ref) < F32_GRAD and rel_err(og.grad, dy_ref) < F32_GRAD
+    else:
+        assert close(dist.float().sum().item(), d_ref.sum().item(), BF16_LOSS_RTOL)
+        assert rel_err(tg.grad, dx_ref) < BF16_GRAD and rel_err(og.grad, dy_ref) < BF16_GRAD
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ot_big_plan_solver(dtype):
+    """64 x 1000: the plan fits neither registers nor shared memory -> the global-scratch solver."""
+    B, M, N, D = 3, 64, 1000, 64
+    txt, obj, tnum, onum = syn.ot_inputs(B, M, N, D, 19, "ragged", dtype=dtype)
+    tp, ip = tnum == 0, onum[:, 1:] == 0
+    d_ref, dx_ref, dy_ref = orc.ot_closed_form_grads(txt.double(), obj.double()[:, 1:], tp, ip,
+                                                     torch.full((B,), 0.01, dtype=torch.float64))
+    tg, og = txt.cuda().requires_grad_(True), obj.cuda().requires_grad_(True)
+    loss, dist = F_.ot_alignment(tg, og, tnum.cuda(), onum.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    lt, gt = (F32_LOSS_RTOL, F32_GRAD) if dtype == torch.float32 else (BF16_LOSS_RTOL, BF16_GRAD)
+    assert close(loss.item(), 0.01 * d_ref.sum().item(), lt)
+    assert rel_err(tg.grad, dx_ref) < gt and rel_err(og.grad[:, 1:], dy_ref) < gt
+
+
+# ------------------------------------------------------------------------------------------
+# production temperature: CLIP checkpoints carry exp(logit_scale) = 100 -> the epilogue's online-max
+# path (the fixed-reference shortcut only holds for s <= 27.7)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,D,kind", [(96, 5, 512, "trained"), (130, 7, 768, "trained"), (256, 9, 512, "iid")])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_contrastive_at_temperature_100(B, T, D, kind, dtype):
+    img, txt, _ = syn.contrastive_inputs(B, T, D, 23, kind, dtype=dtype)
+    ls = torch.tensor(math.log(100.0))
+    lpi, lpt, idx = syn.contrastive_labels(B, T)
+    ri, rt, rdi, rdt, rdls = orc.contrastive_closed_form(img.double(), txt.double(), ls.double(), lpi, lpt, idx)
+    ig, tg, lsg = img.cuda().requires_grad_(True), txt.cuda().requires_grad_(True), ls.cuda().requires_grad_(True)
+    li, lt = F_.contrastive_over_batch(ig, tg, lsg, lpi.cuda(), lpt.cuda(), idx.cuda())
+    (li + lt).backward()
+    torch.cuda.synchronize()
+    if dtype == torch.float32:
+        # a logit of magnitude 100 has an fp32 resolution of 8e-6: the absolute term scales with the temperature
+        assert close(li.item(), ri, F32_LOSS_RTOL, 2e-5) and close(lt.item(), rt, F32_LOSS_RTOL, 2e-5)
+        # exp() arguments carry 7x the absolute error they have at s = 14.3: the gradients are held to 3e-4
+        assert rel_err(ig.grad, rdi) < 3e-4 and rel_err(tg.grad, rdt) < 3e-4
+        assert close(lsg.grad.item(), rdls, 1e-3, 1e-4)
+    else:
+        assert close(li.item(), ri, 1e-2, 2e-3) and close(lt.item(), rt, 1e-2, 2e-3)
+        assert rel_err(ig.grad, rdi) < 3e-2 and rel_err(tg.grad, rdt) < 3e-2
+
+
+# ------------------------------------------------------------------------------------------
+# input validation: what raises an IndexError in the reference comes back as NaN losses (no host sync)
+# ------------------------------------------------------------------------------------------
+def test_contrastive_index_errors_give_nan_not_garbage():
+    B, T, D = 16, 3, 64
+    img, txt, ls = syn.contrastive_inputs(B, T, D, 1, "iid")
+    lpi, lpt, idx = syn.contrastive_labels(B, T)
+    img, txt, ls = img.cuda(), txt.cuda(), ls.cuda()
+
+    def losses(lpi_, lpt_, idx_):
+        a, b = F_.contrastive_over_batch(img, txt, ls, lpi_.cuda(), lpt_.cuda(), idx_.cuda())
+        return a.item(), b.item()
+
+    ok = losses(lpi, lpt, idx)
+    assert all(math.isfinite(v) for v in ok)
+    bad_idx = idx.clone(); bad_idx[3] = B * T + 5
+    assert all(math.isnan(v) for v in losses(lpi, lpt, bad_idx))
+    neg_idx = idx.clone(); neg_idx[0] = -1
+    assert all(math.isnan(v) for v in losses(lpi, lpt, neg_idx))
+    dup_idx = idx.clone(); dup_idx[5] = dup_idx[4]
+    assert all(math.isnan(v) for v in losses(lpi, lpt, dup_idx))
+    bad_lab = lpi.clone(); bad_lab[2] = B * T
+    assert all(math.isnan(v) for v in losses(bad_lab, lpt, idx))
+    bad_lpt = lpt.clone(); bad_lpt[idx[1]] = B + 3
+    assert all(math.isnan(v) for v in losses(lpi, bad_lpt, idx))
+    assert losses(lpi, lpt, idx) == ok                               # and the next call is clean again
+    with pytest.raises(RuntimeError, match="one entry per description"):
+        losses(lpi, torch.arange(B), idx)                            # the reference's default labels_per_text with T > 1
+    with pytest.raises(RuntimeError, match="index_pos is empty"):
+        losses(lpi, lpt, idx[:0])
+    os.environ["CE_CHECK_INPUTS"] = "1"
+    try:
+        with pytest.raises(RuntimeError, match="out of range"):
+            losses(lpi, lpt, bad_idx)
+    finally:
+        del os.environ["CE_CHECK_INPUTS"]
+
+
+# ------------------------------------------------------------------------------------------
+# CriterionContrastive on materialised logits (model_clip.py:633-662 accepts any tensors)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T", [(24, 5), (64, 9), (7, 3)])
+def test_dense_logits_criterion(dtype, B, T):
+    g = torch.Generator().manual_seed(4)
+    lpi_logits = (3 * torch.randn(B, B * T, generator=g)).to(dtype)
+    lpt_logits = (3 * torch.randn(B * T, B, generator=g)).to(dtype)
+    lpi, lpt, idx = syn.contrastive_labels(B, T)
+    idx = torch.cat([idx, idx[:2]])                                   # rows named twice accumulate, like index_select
+    a = lpi_logits.double().requires_grad_(True)
+    b = lpt_logits.double().requires_grad_(True)
+    ref = orc.contrastive_criterion(a, b, lpi, lpt, idx, True, "ce")
+    (ref["loss_i"] + 0.5 * ref["loss_t"]).backward()
+    ag, bg = lpi_logits.cuda().requires_grad_(True), lpt_logits.cuda().requires_grad_(True)
+    out = ce.CriterionContrastive("ce")(ag, bg, lpi.cuda(), lpt.cuda(), index_pos=idx.cuda())
+    assert out["loss_i"].dtype == dtype
+    (out["loss_i"].float() + 0.5 * out["loss_t"].float()).backward()
+    torch.cuda.synchronize()
+    lt, gt = (1e-5, 2e-5) if dtype == torch.float32 else (1e-2, 1e-2)
+    assert close(out["loss_i"].item(), ref["loss_i"].item(), lt, 1e-5) and close(out["loss_t"].item(), ref["loss_t"].item(), lt, 1e-5)
+    assert rel_err(ag.grad, a.grad) < gt and rel_err(bg.grad, b.grad) < gt
+
+
+def test_dense_logits_bce_and_errors():
+    B, T = 12, 4
+    g = torch.Generator().manual_seed(6)
+    li = 2 * torch.randn(B, T, generator=g)
+    lt = 2 * torch.randn(B * T, B, generator=g)
+    y = torch.zeros(B, T); y[:, 0] = 1
+    _, lpt, idx = syn.contrastive_labels(B, T)
+    a, b = li.double().requires_grad_(True), lt.double().requires_grad_(True)
+    ref = orc.contrastive_criterion(a, b, y.double(), lpt, idx, False, "bce")
+    sum(ref.values()).backward()
+    ag, bg = li.cuda().requires_grad_(True), lt.cuda().requires_grad_(True)
+    out = ce.CriterionContrastive("bce")(ag, bg, y.cuda(), lpt.cuda(), index_pos=idx.cuda(), constrastive_overbatch=False)
+    sum(out.values()).backward()
+    assert close(out["loss_i"].item(), ref["loss_i"].item(), 1e-5, 1e-6) and close(out["loss_t"].item(), ref["loss_t"].item(), 1e-5, 1e-6)
+    assert rel_err(ag.grad, a.grad) < 2e-5 and rel_err(bg.grad, b.grad) < 2e-5
+    bad = idx.clone(); bad[1] = B * T
+    out = ce.CriterionContrastive("ce")(lt.t().contiguous().cuda(), lt.cuda(), idx.cuda() // T * 0, lpt.cuda(), index_pos=bad.cuda())
+    assert math.isnan(out["loss_t"].item())
+
+
+# ------------------------------------------------------------------------------------------
+# CriterionAlignment reads *_num masks (nonzero = valid) whatever their dtype
+# ------------------------------------------------------------------------------------------
+def test_alignment_bool_masks_mean_valid():
+    txt, obj, tnum, onum = syn.ot_inputs(9, 8, 20, 64, 3, "ragged")
+    crit = ce.CriterionAlignment()
+    a = crit(txt.cuda(), obj.cuda(), tnum.cuda(), onum.cuda())["loss_ot"].item()
+    b = crit(txt.cuda(), obj.cuda(), tnum.bool().cuda(), onum.bool().cuda())["loss_ot"].item()
+    c = crit(txt.cuda(), obj.cuda(), tnum.to(torch.uint8).cuda(), onum.float().cuda())["loss_ot"].item()
+    ref = orc.alignment_criterion(txt, obj, tnum, onum)["loss_ot"].item()
+    assert a == b == c and close(a, ref, F32_LOSS_RTOL)
+
+
+# ------------------------------------------------------------------------------------------
+# the one-call step == the two criteria called one after the other
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_loss_head_step_equals_separate_criteria(dtype):
+    w = syn.WORKLOADS["c2"]
+    img, txt, _ = syn.contrastive_inputs(w.B, w.T, w.D, 8, "trained", dtype=dtype)
+    lpi, lpt, idx = (t.cuda() for t in syn.contrastive_labels(w.B, w.T))
+    etxt, obj, tnum, onum = syn.ot_inputs(w.B, w.M, w.N, w.D, 9, "ragged", dtype=dtype)
+    tnum, onum = tnum.cuda(), onum.cuda()
+
+    def leaves():
+        return [t.cuda().requires_grad_(True) for t in (img, txt, etxt, obj)]
+
+    head = ce.ClipEventHead().cuda()
+    a = leaves()
+    lpi_l, lpt_l = head(a[0], a[1])
+    ld = ce.CriterionContrastive("ce")(lpi_l, lpt_l, lpi, lpt, index_pos=idx)
+    ld.update(ce.CriterionAlignment()(a[2], a[3], tnum, onum))
+    sum(ld.values()).backward()
+    g_sep = [t.grad.clone() for t in a] + [head.logit_scale.grad.clone()]
+    head.logit_scale.grad = None
+    b = leaves()
+    ld2 = ce.LossHeadStep(head)(b[0], b[1], lpi, lpt, idx, b[2], b[3], tnum, onum)
+    sum(ld2.values()).backward()
+    torch.cuda.synchronize()
+    for k in ("loss_i", "loss_t", "loss_ot"):
+        assert ld[k].item() == ld2[k].item() and ld2[k].dtype == dtype
+    for x, y in zip(g_sep, [t.grad for t in b] + [head.logit_scale.grad]):
+        assert torch.equal(x, y)
+    # scaled upstream gradient: both contrastive losses by the same factor
+    c = leaves()
+    ld3 = ce.LossHeadStep(head)(c[0], c[1], lpi, lpt, idx, c[2], c[3], tnum, onum)
+    (2.0 * (ld3["loss_i"].float() + ld3["loss_t"].float()) - 0.5 * ld3["loss_ot"].float()).backward()
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    assert rel_err(c[0].grad, 2.0 * g_sep[0].float()) < tol and rel_err(c[2].grad, -0.5 * g_sep[2].float()) < tol
+    # different factors cannot be honoured by the fused gradients: NaN, never a silently wrong number
+    d = leaves()
+    ld4 = ce.LossHeadStep(head)(d[0], d[1], lpi, lpt, idx, d[2], d[3], tnum, onum)
+    (ld4["loss_i"].float() + 3.0 * ld4["loss_t"].float()).backward()
+    assert torch.isnan(d[0].grad.float()).all() and d[2].grad is None
+    e = leaves()
+    ld5 = ce.LossHeadStep(head)(e[0], e[1], lpi, lpt, idx, e[2], e[3], tnum, onum)
+    with pytest.raises(RuntimeError, match="together"):
+        ld5["loss_i"].float().backward()
+
+
+# ------------------------------------------------------------------------------------------
+# the shared-memory-resident OT kernel (opt-in while the three-kernel path is faster): parity at every
+# shape class it accepts, 10/25/100 iterations, both beta
+# ------------------------------------------------------------------------------------------
+def test_fused_ot_kernel_parity():
+    env = dict(os.environ, CE_OT_FUSED="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ot_fused_check.py")], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "ALL OK" in r.stdout and "BAD" not in r.stdout, r.stdout[-3000:]

@@ -15,10 +15,23 @@ def test_criterion_contrastive_rejects_unknown_loss_like_the_reference():
         ce.CriterionContrastive(ok)
 
 
-def test_criterion_contrastive_needs_lazy_logits():
+def test_criterion_contrastive_accepts_dense_logits_but_has_no_cpu_path():
+    # model_clip.py:633-662 takes any logits tensors; the drop-in does too (CUDA row kernels) -- on CPU
+    # tensors it raises instead of falling back
     crit = ce.CriterionContrastive("ce")
-    with pytest.raises(RuntimeError, match="LazyLogits"):
-        crit(torch.randn(2, 4), torch.randn(4, 2), index_pos=torch.tensor([0, 2]))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        crit(torch.randn(2, 4), torch.randn(4, 2), torch.tensor([0, 2]), torch.tensor([0, 0, 1, 1]), index_pos=torch.tensor([0, 2]))
+    with pytest.raises(RuntimeError, match="global negatives need the features"):
+        ce.CriterionContrastive("ce", group=True)(torch.randn(2, 4), torch.randn(4, 2), index_pos=torch.tensor([0, 2]))
+
+
+def test_alignment_masks_are_num_semantics_for_every_dtype():
+    # the reference applies mask2pad(x) = (x == 0) whatever the dtype (model_clip.py:673-676,688-690)
+    from clip_event_b200 import functional as F_
+    b = torch.tensor([[True, False]])
+    assert F_.num_mask(b).dtype == torch.int64 and F_.num_mask(b).tolist() == [[1, 0]]
+    i = torch.tensor([[1, 0]])
+    assert F_.num_mask(i) is i
 
 
 def test_lazy_logits_shapes():
@@ -92,5 +105,10 @@ def test_bench_reference_arm_contract():
     assert line["higher_is_better"] is True and line["n_gpus"] >= 1 and line["value"] > 0
     assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     assert "workload" in line["config"]
+    # both arms print the same workload description
+    sys.path.insert(0, root)
+    import bench
+    from clip_event_b200 import synthetic as syn_
+    assert line["config"] == bench.config_dict(syn_.WORKLOADS["c1"], 1, "bf16")
