@@ -346,7 +346,6 @@ def dist_parity(world, rank, dev, dtype):
     (bench workload size, same dtype) and (b) the fp64 closed-form oracle at a reduced size.  Every rank
     checks its own slices; the worst relative error over the ranks is reported."""
     import torch.distributed as dist
-    import clip_event_b200 as ce
     from clip_event_b200 import distributed as cd
     from oracle import clip_event_oracle as orc
 
@@ -354,25 +353,28 @@ def dist_parity(world, rank, dev, dtype):
         a, b = a.detach().double().flatten(), b.detach().double().flatten()
         return float(((a - b).norm() / b.norm().clamp_min(1e-30)).item())
 
+    from clip_event_b200 import functional as F_
+
     def run_pair(B, T, D, M, N, seed, with_oracle):
+        """fp32 losses from the functional layer (the modules cast them to the input dtype, as the reference does)."""
         img, txt, ls = syn.contrastive_inputs(B, T, D, seed, "trained", dtype=dtype)
         etxt, obj, tnum, onum = syn.ot_inputs(B, M, N, D, seed + 1, "ragged", dtype=dtype)
         lo, hi = cd.shard_bounds(B, world, rank)
         b = hi - lo
-        lpi, lpt, idx = (t.to(dev) for t in syn.contrastive_labels(b, T))
-        head = ce.ClipEventHead().to(dev)
-        sh = ce.LossHeadStep(head, group=True, ddp_average=False)
+        lpi, lpt, idx = cd.global_labels_for_rank(b, T, world, rank, device=dev)
         lv = dict(img=img[lo:hi], txt=txt[lo * T:hi * T], etxt=etxt[lo:hi], obj=obj[lo:hi])
         lv = {k: v.to(dev).requires_grad_(True) for k, v in lv.items()}
-        ld = sh(lv["img"], lv["txt"], lpi, lpt, idx, lv["etxt"], lv["obj"], tnum[lo:hi].to(dev), onum[lo:hi].to(dev))
+        lsg = ls.to(dev).requires_grad_(True)
+        ld = dict(zip(("loss_i", "loss_t", "loss_ot"), cd.global_loss_head_step(
+            lv["img"], lv["txt"], lsg, lpi, lpt, idx, lv["etxt"], lv["obj"], tnum[lo:hi].to(dev), onum[lo:hi].to(dev))))
         sum(ld.values()).backward()
         # single-GPU CUDA path on the whole batch (every rank computes it; it fits one GPU)
-        head1 = ce.ClipEventHead().to(dev)
-        s1 = ce.LossHeadStep(head1)
         fl = dict(img=img, txt=txt, etxt=etxt, obj=obj)
         fl = {k: v.to(dev).requires_grad_(True) for k, v in fl.items()}
+        ls1 = ls.to(dev).requires_grad_(True)
         gl = [t.to(dev) for t in syn.contrastive_labels(B, T)]
-        ld1 = s1(fl["img"], fl["txt"], gl[0], gl[1], gl[2], fl["etxt"], fl["obj"], tnum.to(dev), onum.to(dev))
+        ld1 = dict(zip(("loss_i", "loss_t", "loss_ot"), F_.loss_head_step(
+            fl["img"], fl["txt"], ls1, gl[0], gl[1], gl[2], fl["etxt"], fl["obj"], tnum.to(dev), onum.to(dev))))
         sum(ld1.values()).backward()
         torch.cuda.synchronize()
         errs = {
@@ -381,7 +383,7 @@ def dist_parity(world, rank, dev, dtype):
             "loss_ot": abs(ld["loss_ot"].item() - ld1["loss_ot"].item()) / max(abs(ld1["loss_ot"].item()), 1e-30),
             "dimg": rel(lv["img"].grad, fl["img"].grad[lo:hi]), "dtxt": rel(lv["txt"].grad, fl["txt"].grad[lo * T:hi * T]),
             "detxt": rel(lv["etxt"].grad, fl["etxt"].grad[lo:hi]), "dobj": rel(lv["obj"].grad, fl["obj"].grad[lo:hi]),
-            "dls": abs(head.logit_scale.grad.item() - head1.logit_scale.grad.item()) / max(1.0, abs(head1.logit_scale.grad.item())),
+            "dls": abs(lsg.grad.item() - ls1.grad.item()) / max(1.0, abs(ls1.grad.item())),
         }
         if with_oracle:
             glc = syn.contrastive_labels(B, T)
@@ -391,10 +393,11 @@ def dist_parity(world, rank, dev, dtype):
                                                              torch.full((B,), 0.01, dtype=torch.float64))
             errs.update({
                 "oracle_loss_i": abs(ld["loss_i"].item() - ri.item()) / abs(ri.item()),
+                "oracle_loss_t": abs(ld["loss_t"].item() - rt.item()) / max(abs(rt.item()), 1e-2),
                 "oracle_loss_ot": abs(ld["loss_ot"].item() - 0.01 * d_ref.sum().item()) / abs(0.01 * d_ref.sum().item()),
                 "oracle_dimg": rel(lv["img"].grad.cpu(), rdi[lo:hi]), "oracle_dtxt": rel(lv["txt"].grad.cpu(), rdt[lo * T:hi * T]),
                 "oracle_detxt": rel(lv["etxt"].grad.cpu(), dx_ref[lo:hi]), "oracle_dobj": rel(lv["obj"].grad[:, 1:].cpu(), dy_ref[lo:hi]),
-                "oracle_dls": abs(head.logit_scale.grad.item() - rdls.item()) / max(1.0, abs(rdls.item())),
+                "oracle_dls": abs(lsg.grad.item() - rdls.item()) / max(1.0, abs(rdls.item())),
             })
         return errs
 

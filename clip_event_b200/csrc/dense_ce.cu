@@ -192,3 +192,62 @@ extern "C" int ce_dense_ce_bwd(const void* logits, int64_t ld, int64_t rows_tota
   CE_LAUNCH_CHECK();
   return CE_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// engine.py:89-90 for the loss head's own parameter: torch.nn.utils.clip_grad_norm_(params, max_norm)
+// followed by optimizer.step() (torch.optim.SGD with momentum / torch.optim.Adam, engine.py:133-149),
+// on the scalar logit_scale.  One launch instead of the dozen element-wise launches the foreach
+// optimiser spends on a one-element tensor; the clip coefficient uses the squared gradient norm of
+// all OTHER parameters (the encoders', computed by the caller) plus this parameter's own.
+// ------------------------------------------------------------------------------------------
+namespace ce {
+namespace {
+__global__ void head_param_step_kernel(float* p, float* grad, float* s0, float* s1, float* step,
+                                       const float* other_sq, float max_norm, int kind, float lr, float b1,
+                                       float b2, float eps, float wd, float* clip_coef_out) {
+  float g = *grad;
+  float coef = 1.f;
+  if (max_norm > 0.f) {
+    const float total = sqrtf((other_sq != nullptr ? *other_sq : 0.f) + g * g);
+    coef = fminf(max_norm / (total + 1e-6f), 1.f);       // clip_grad_norm_: clamp(max_norm / (norm + 1e-6), max = 1)
+    g *= coef;
+    *grad = g;                                            // the reference scales .grad in place
+  }
+  if (clip_coef_out != nullptr) *clip_coef_out = coef;
+  float w = *p;
+  const float t = *step + 1.f;
+  *step = t;
+  if (wd != 0.f) g = fmaf(wd, w, g);                      // L2 weight decay as both optimisers apply it
+  if (kind == 0) {                                        // torch.optim.SGD(momentum = b1)
+    float buf = g;
+    if (b1 != 0.f) {
+      buf = t == 1.f ? g : fmaf(b1, *s0, g);
+      *s0 = buf;
+    }
+    w -= lr * buf;
+  } else {                                                // torch.optim.Adam
+    const float m = fmaf(b1, *s0, (1.f - b1) * g);        // lerp(exp_avg, g, 1 - b1)
+    const float v = fmaf(b2, *s1, (1.f - b2) * g * g);
+    *s0 = m; *s1 = v;
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float denom = sqrtf(v) / sqrtf(bc2) + eps;
+    w -= (lr / bc1) * (m / denom);
+  }
+  *p = w;
+}
+}  // namespace
+}  // namespace ce
+
+extern "C" int ce_head_param_step(float* param, float* grad, float* state0, float* state1, float* step,
+                                  const float* other_grad_sq, float max_norm, int kind, float lr,
+                                  float beta1, float beta2, float eps, float weight_decay,
+                                  float* clip_coef_out, ce_stream_t stream) {
+  CE_TRY(check_device());
+  if (kind != 0 && kind != 1) return fail(CE_ERR_ARG, "head_param_step: kind must be 0 (SGD) or 1 (Adam)");
+  if (param == nullptr || grad == nullptr || state0 == nullptr || step == nullptr || (kind == 1 && state1 == nullptr))
+    return fail(CE_ERR_ARG, "head_param_step: null parameter / gradient / optimiser state");
+  head_param_step_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      param, grad, state0, state1, step, other_grad_sq, max_norm, kind, lr, beta1, beta2, eps, weight_decay, clip_coef_out);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}

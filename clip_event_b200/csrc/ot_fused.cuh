@@ -24,6 +24,7 @@ struct OtFusedArgs {
   void* dslot0;               // nullable: [B] rows of D elements, stride img_bs, zero-filled
   int slots;                  // filled in by the launcher
   int poll_mode;              // debug (CE_OT_POLL)
+  int dbg;                    // debug (CE_OT_DBG): 1 = no MMA work, 2 = no bulk copies (results are garbage)
   long long* trace;           // debug timeline buffer (CE_OT_TRACE_PTR), normally null
 };
 

@@ -473,3 +473,41 @@ def loss_head_step(image_features, text_features, logit_scale, labels_per_image,
     """(loss_i, loss_t, loss_ot) of the whole loss head in one call; see :class:`_LossHeadStep`."""
     return _LossHeadStep.apply(image_features, text_features, logit_scale, entitytxt_vec, object_vec,
                                labels_per_image, labels_per_text, index_pos, entitytxt_num, object_num, image_loss)
+
+
+# --------------------------------------------------------------------------------------------
+# engine.py:89-90 for the head's own parameter (SURVEY.md 8f-4)
+# --------------------------------------------------------------------------------------------
+class HeadParamStep:
+    """``clip_grad_norm_(params, max_norm)`` + ``optimizer.step()`` for ``logit_scale`` in ONE launch.
+
+    ``kind``: 'sgd' (torch.optim.SGD, momentum) or 'adam' (torch.optim.Adam), the two optimisers
+    engine.build_optimizer offers (engine.py:133-149).  ``other_grad_sq`` is the squared gradient norm
+    of all other parameters (a device scalar; None = the head's parameter is clipped alone).  Returns
+    the clip coefficient (device scalar) for the caller's other parameters.
+    """
+
+    def __init__(self, param: torch.Tensor, kind="adam", lr=1e-6, momentum=0.9, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=0.0, max_norm=1.0):
+        L.require_cuda(param)
+        if param.numel() != 1 or param.dtype != torch.float32:
+            raise RuntimeError("HeadParamStep drives the scalar fp32 logit_scale parameter")
+        if kind not in ("sgd", "adam"):
+            raise RuntimeError("Invalid optimizer '{}'. ".format(kind))      # engine.py:149
+        self.param, self.kind = param, kind
+        self.lr, self.eps, self.wd, self.max_norm = lr, eps, weight_decay, max_norm
+        self.b1, self.b2 = (momentum, 0.0) if kind == "sgd" else betas
+        self.state = torch.zeros(4, dtype=torch.float32, device=param.device)    # state0, state1, step, clip_coef
+
+    @torch.no_grad()
+    def step(self, other_grad_sq: Optional[torch.Tensor] = None, lr: Optional[float] = None):
+        g = self.param.grad
+        if g is None:
+            raise RuntimeError("logit_scale has no gradient")
+        st = self.state
+        o = None if other_grad_sq is None else _scalar_f32(other_grad_sq, st.device)
+        L.check(L.load().ce_head_param_step(
+            self.param.data_ptr(), g.data_ptr(), st.data_ptr(), st.data_ptr() + 4, st.data_ptr() + 8, L.ptr(o),
+            float(self.max_norm), 0 if self.kind == "sgd" else 1, float(self.lr if lr is None else lr), float(self.b1),
+            float(self.b2), float(self.eps), float(self.wd), st.data_ptr() + 12, L.stream_ptr()), "head parameter step")
+        return st[3]

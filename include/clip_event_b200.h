@@ -223,6 +223,24 @@ int ce_dense_ce_bwd(const void* logits, int64_t ld, int64_t rows_total, int cols
                     int dtype, const float* g, float* dlogits, int64_t ldd, const void* workspace,
                     ce_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The step either side of the path, for the loss head's OWN parameter logit_scale:
+ * torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm) + optimizer.step()  (engine.py:89-90,
+ * optimisers built at engine.py:133-149) in one launch.  All pointers are fp32 device scalars.
+ *   other_grad_sq   nullable: sum of squared gradients of every OTHER parameter (the encoders');
+ *                   total_norm = sqrt(other_grad_sq + grad^2), clip_coef = min(1, max_norm/(total_norm+1e-6));
+ *                   max_norm <= 0 disables clipping.  *grad is scaled in place, as the reference does.
+ *   kind 0          torch.optim.SGD:  g += wd p; buf = (step 1 ? g : beta1 buf + g); p -= lr buf
+ *                   (state0 = momentum buffer, beta1 = momentum; beta1 = 0: no buffer)
+ *   kind 1          torch.optim.Adam: g += wd p; state0/state1 = exp_avg / exp_avg_sq; bias-corrected
+ *   step            fp32 counter, incremented here;  clip_coef_out nullable (the encoders' gradients
+ *                   need the same coefficient).
+ * ------------------------------------------------------------------------------------------ */
+int ce_head_param_step(float* param, float* grad, float* state0, float* state1, float* step,
+                       const float* other_grad_sq, float max_norm, int kind, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, float* clip_coef_out,
+                       ce_stream_t stream);
+
 /* Number of kernels this library has launched in this process (for benchmark bookkeeping). */
 unsigned long long ce_debug_launch_count(void);
 

@@ -248,3 +248,30 @@ def test_fused_ot_kernel_parity():
                        timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "ALL OK" in r.stdout and "BAD" not in r.stdout, r.stdout[-3000:]
+
+
+# ------------------------------------------------------------------------------------------
+# engine.py:89-90 on the head's own parameter: clip_grad_norm_ + optimizer.step() in one launch
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["sgd", "adam"])
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_head_param_step_matches_torch_optim(kind, wd):
+    torch.manual_seed(0)
+    p_ref = torch.nn.Parameter(torch.tensor(2.6593, device="cuda"))
+    other = torch.nn.Parameter(torch.randn(100, device="cuda"))
+    p_new = torch.nn.Parameter(p_ref.detach().clone())
+    if kind == "sgd":
+        opt = torch.optim.SGD([p_ref, other], lr=1e-2, momentum=0.9, weight_decay=wd)
+    else:
+        opt = torch.optim.Adam([p_ref, other], lr=1e-2, weight_decay=wd)
+    stepper = F_.HeadParamStep(p_new, kind=kind, lr=1e-2, momentum=0.9, weight_decay=wd, max_norm=1.0)
+    for it in range(6):
+        g = torch.tensor(0.3 * (it + 1) * (-1) ** it, device="cuda")
+        og = torch.randn(100, device="cuda") * (0.05 if it % 2 else 0.5)      # clipped and unclipped steps
+        p_ref.grad, other.grad, p_new.grad = g.clone(), og.clone(), g.clone()
+        torch.nn.utils.clip_grad_norm_([p_ref, other], 1)                      # engine.py:89
+        opt.step()                                                             # engine.py:90
+        coef = stepper.step(other_grad_sq=(og.float() ** 2).sum())
+        assert abs(p_new.item() - p_ref.item()) <= 2e-6 * max(1.0, abs(p_ref.item())), (it, p_new.item(), p_ref.item())
+        assert abs(p_new.grad.item() - p_ref.grad.item()) <= 1e-6 * max(1.0, abs(p_ref.grad.item()))
+        assert abs((og * coef).norm().item() - other.grad.norm().item()) <= 1e-5

@@ -76,6 +76,22 @@ if __name__ == "__main__":
     for iters in (10, 25, 100):
         for beta in (0.3, 0.5):
             ok = check(64, 16, 50, 512, "ragged", "iid", iters, beta) and ok
+    # bench size (28 samples per CTA: the steady state of the job ring) against the fp64 oracle on a slice of CTA 0 .. 147's samples
+    w = syn.WORKLOADS["c3"]
+    txt, obj, tnum, onum = syn.ot_inputs(w.B, w.M, w.N, w.D, 0, "ragged", dtype=torch.bfloat16)
+    t, o = txt.cuda().requires_grad_(True), obj.cuda().requires_grad_(True)
+    loss, dist = F_.ot_alignment(t, o, tnum.cuda(), onum.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    sel = torch.arange(0, w.B, 13)
+    tp, ip = tnum[sel] == 0, onum[sel][:, 1:] == 0
+    d_ref, dx_ref, dy_ref = orc.ot_closed_form_grads(txt[sel].double(), obj[sel].double()[:, 1:], tp, ip,
+                                                     torch.full((sel.numel(),), 0.01, dtype=torch.float64))
+    e = dict(dist=rel(dist.cpu()[sel], d_ref), dtxt=rel(t.grad.cpu()[sel], dx_ref), dobj=rel(o.grad.cpu()[sel][:, 1:], dy_ref),
+             finite=bool(torch.isfinite(t.grad).all() and torch.isfinite(o.grad).all()), loss=float(loss))
+    good = e["dist"] < 1e-4 and e["dtxt"] < 1e-2 and e["dobj"] < 1e-2 and e["finite"] and abs(e["loss"] - 39.0049) < 0.05
+    print("%s c3 full size: %s" % ("OK " if good else "BAD", " ".join("%s=%.3e" % kv for kv in e.items())), flush=True)
+    ok = ok and good
     print("ALL OK" if ok else "SOME BAD", flush=True)
     if len(sys.argv) > 1:
         timeit("c3")

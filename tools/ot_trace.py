@@ -12,9 +12,14 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else w.B
 etxt, obj, tnum, onum = syn.ot_inputs(B, w.M, w.N, w.D, 0, "ragged", dtype=torch.bfloat16)
 eg, og = etxt.cuda().requires_grad_(True), obj.cuda().requires_grad_(True)
 tnum, onum = tnum.cuda(), onum.cuda()
+nograd = len(sys.argv) > 3 and sys.argv[3] == "nograd"
 for _ in range(2):
     buf.zero_()
-    l, _ = F_.ot_alignment(eg, og, tnum, onum)
+    if nograd:
+        with torch.no_grad():
+            l, _ = F_.ot_alignment(eg.detach(), og.detach(), tnum, onum)
+    else:
+        l, _ = F_.ot_alignment(eg, og, tnum, onum)
     torch.cuda.synchronize()
 t = buf.cpu().view(64, 32)
 base = int(t[0, 0])
