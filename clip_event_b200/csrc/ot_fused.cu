@@ -271,14 +271,14 @@ __global__ void __launch_bounds__(kThreads, 1) ot_fused_kernel(const OtFusedArgs
         tma_store_commit();
       }
       __syncwarp();
+      tma_store_wait_read();                       // the gradient slot has been read out: hand it back first
+      OT_TRACE(k, 2);
+      if (k + 1 < count) named_arrive(9);
       // sample k+P was parked at the end of this gradient job: its cost slot takes sample k+P+2
       if (k + P + 2 < count) {
         named_sync(11 + ((k + P) & 1));
         issue_load(k + P + 2);
       }
-      tma_store_wait_read();                       // the gradient slot has been read out
-      OT_TRACE(k, 2);
-      if (k + 1 < count) named_arrive(9);
     }
     tma_store_wait_all();
   } else if (warp < 4) {

@@ -1351,8 +1351,8 @@ extern "C" int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* i
     return CE_OK;
   }
   // Small plans in bf16: ONE persistent kernel keeps x, y resident in shared memory from the load to
-  // the gradient store (csrc/ot_fused.cu).  Opt-in through CE_OT_FUSED=1 while it is slower than the three-kernel path.
-  static const bool fused_ok = [] { const char* e = getenv("CE_OT_FUSED"); return e != nullptr && atoi(e) != 0; }();
+  // the gradient store (csrc/ot_fused.cu).  CE_OT_FUSED=0 (debug switch) forces the three-kernel path.
+  static const bool fused_ok = [] { const char* e = getenv("CE_OT_FUSED"); return e == nullptr || atoi(e) != 0; }();
   if (fused_ok && ot_fused_supported(M, N, D, dtype)) {
     OtFusedArgs fa{};
     fa.txt = txt; fa.img = img; fa.txt_bs = txt_bstride; fa.img_bs = img_bstride;

@@ -219,8 +219,10 @@ def test_loss_head_step_equals_separate_criteria(dtype):
     torch.cuda.synchronize()
     for k in ("loss_i", "loss_t", "loss_ot"):
         assert ld[k].item() == ld2[k].item() and ld2[k].dtype == dtype
+    # same kernels, same inputs; not bit-identical run to run because split-K partial sums meet in red.add
+    same = 2e-6 if dtype == torch.float32 else 1e-4
     for x, y in zip(g_sep, [t.grad for t in b] + [head.logit_scale.grad]):
-        assert torch.equal(x, y)
+        assert rel_err(x, y) < same
     # scaled upstream gradient: both contrastive losses by the same factor
     c = leaves()
     ld3 = ce.LossHeadStep(head)(c[0], c[1], lpi, lpt, idx, c[2], c[3], tnum, onum)
