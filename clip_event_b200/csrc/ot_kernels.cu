@@ -1233,6 +1233,10 @@ int make_plan(int M, int N, OtPlan* p) {
   if (ntiles <= 4) { p->nwarps = 4; p->tpw = 1; }
   else { p->nwarps = 8; p->tpw = p->MP == 64 ? 2 : 3; }
   int cap = p->nwarps * p->tpw;
+  {   // tuning aid: CE_OT_CAP limits the 16-row tiles per CTA (more, smaller CTAs per sample)
+    static const int cap_env = [] { const char* e = getenv("CE_OT_CAP"); return e != nullptr ? atoi(e) : 0; }();
+    if (cap_env > 0 && cap_env < cap) cap = cap_env;
+  }
   p->nsplit = (ntiles + cap - 1) / cap;
   p->tiles_per_cta = (ntiles + p->nsplit - 1) / p->nsplit;
   int rows = p->tiles_per_cta * 16;

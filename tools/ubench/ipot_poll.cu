@@ -4,6 +4,9 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include <cstdint>
+#ifndef BIG
+#define BIG 0
+#endif
 constexpr int kPLd = 18, kMP = 16;
 __device__ __forceinline__ float frcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 struct Scr { float P[32 * kPLd]; float w[16]; float v[16]; };
@@ -14,7 +17,9 @@ __device__ __forceinline__ bool try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __global__ void __launch_bounds__(384, 1) k(long long* out, float* sink, int iters, int mode) {
-  __shared__ __align__(16) Scr scr[3];
+  extern __shared__ __align__(128) unsigned char dyn[];
+  // same placement as in ot_fused_kernel: scratch blocks behind 208 000 bytes of sample slots, 7872 bytes apart
+  auto scr_at = [&](int i) -> Scr& { return *reinterpret_cast<Scr*>(dyn + (BIG ? 208000 + 5440 : 0) + (size_t)i * (BIG ? 7872 : sizeof(Scr))); };
   __shared__ uint64_t bar;
   __shared__ volatile int flag;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -28,7 +33,7 @@ __global__ void __launch_bounds__(384, 1) k(long long* out, float* sink, int ite
     else if (mode == 4) { if (lane == 0) { while (!try_wait(&bar, 0)) __nanosleep(2000); } __syncwarp(); }
     return;
   }
-  Scr& sc = scr[wid - 1];
+  Scr& sc = scr_at(wid - 1);
   const int c = lane & 15;
   const float* pcol = sc.P + (lane >> 4) * 16 * kPLd + c;
   const int prot = (lane >> 4) * 8;
@@ -102,12 +107,17 @@ __global__ void __launch_bounds__(384, 1) k(long long* out, float* sink, int ite
   __syncwarp();
   if (lane == 0) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar)) : "memory"); atomicAdd((int*)&flag, 1); }
 }
+#ifndef BIG
+#define BIG 0
+#endif
 int main() {
+  size_t dynb = BIG ? 231616 : 3 * sizeof(Scr);
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynb);
   long long* out; float* sink;
   cudaMalloc(&out, 148 * 4 * 8); cudaMalloc(&sink, 148 * 384 * 4);
   for (int mode = 0; mode < 5; ++mode) {
-    k<<<148, 384>>>(out, sink, 50, mode);
-    k<<<148, 384>>>(out, sink, 50, mode);
+    k<<<148, 384, dynb>>>(out, sink, 50, mode);
+    k<<<148, 384, dynb>>>(out, sink, 50, mode);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[4];
     cudaMemcpy(h, out, 32, cudaMemcpyDeviceToHost);
