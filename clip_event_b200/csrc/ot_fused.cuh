@@ -22,7 +22,8 @@ struct OtFusedArgs {
   void* dtxt;                 // nullable (forward only): same layout as txt
   void* dimg;                 // same layout as img
   void* dslot0;               // nullable: [B] rows of D elements, stride img_bs, zero-filled
-  int slots;                  // filled in by the launcher
+  int slots;                  // filled in by the launcher (fused: resident slots; stream: parks)
+  int cy_depth, gy_depth;     // stream kernel: chunk ring depths of the cost / gradient stage
   int poll_mode;              // debug (CE_OT_POLL)
   int dbg;                    // debug (CE_OT_DBG): 1 = no MMA work, 2 = no bulk copies (results are garbage)
   long long* trace;           // debug timeline buffer (CE_OT_TRACE_PTR), normally null
@@ -33,5 +34,10 @@ bool ot_fused_supported(int M, int N, int D, int dtype);
 int ot_fused_slots(int M, int N, int D);
 size_t ot_fused_smem_bytes(int M, int N, int D, int slots);
 int launch_ot_fused(OtFusedArgs a, cudaStream_t st);
+
+// Streaming variant (csrc/ot_stream.cu): bf16, M <= 16, N <= 64, D a multiple of 64 up to 512
+bool ot_stream_supported(int M, int N, int D, int dtype);
+size_t ot_stream_smem_bytes(int D, int parks, int cy_depth, int gy_depth);
+int launch_ot_stream(OtFusedArgs a, cudaStream_t st);
 
 }  // namespace ce

@@ -1357,14 +1357,18 @@ extern "C" int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* i
   // Small plans in bf16: ONE persistent kernel keeps x, y resident in shared memory from the load to
   // the gradient store (csrc/ot_fused.cu).  CE_OT_FUSED=0 (debug switch) forces the three-kernel path.
   static const bool fused_ok = [] { const char* e = getenv("CE_OT_FUSED"); return e == nullptr || atoi(e) != 0; }();
-  if (fused_ok && ot_fused_supported(M, N, D, dtype)) {
+  // CE_OT_STREAM=0 selects the shared-memory-resident predecessor (csrc/ot_fused.cu) where both apply.
+  static const bool stream_ok = [] { const char* e = getenv("CE_OT_STREAM"); return e == nullptr || atoi(e) != 0; }();
+  const bool use_stream = fused_ok && stream_ok && ot_stream_supported(M, N, D, dtype);
+  if (use_stream || (fused_ok && ot_fused_supported(M, N, D, dtype))) {
     OtFusedArgs fa{};
     fa.txt = txt; fa.img = img; fa.txt_bs = txt_bstride; fa.img_bs = img_bstride;
     fa.txt_mask = txt_mask; fa.img_mask = img_mask; fa.txt_ms = txt_mstride; fa.img_ms = img_mstride;
     fa.mask_kind = mask_kind; fa.B = B; fa.M = M; fa.N = N; fa.D = D;
     fa.beta = beta; fa.eps = 1e-5f; fa.scale = loss_scale; fa.iters = iters; fa.k = k;
     fa.dist = dist; fa.dtxt = dtxt; fa.dimg = dimg; fa.dslot0 = dtxt != nullptr ? dimg_slot0 : nullptr;
-    CE_TRY(launch_ot_fused(fa, st));
+    if (use_stream) CE_TRY(launch_ot_stream(fa, st));
+    else CE_TRY(launch_ot_fused(fa, st));
     ot_tail_kernel<CE_BF16><<<1, 256, 0, st>>>(dist, B, loss_scale, loss, nullptr, img_bstride, D);
     CE_LAUNCH_CHECK();
     return CE_OK;

@@ -24,9 +24,15 @@ for _ in range(2):
 t = buf.cpu().view(64, 32)
 base = int(t[0, 0])
 names = ["ld_issue", "out_rdy", "st_read", "full", "cost_dn", "w_rdy", "dx_dn", "dy_dn", "grad_dn", "s_rdy", "A_dn", "iter_dn", "epi_dn"]
+if os.environ.get("CE_OT_STREAM", "1") != "0":   # csrc/ot_stream.cu events
+    names = ["cld_iss", "gld_iss", "c_xfull", "c_yfull", "c_done", "c_scrfr", "g_wrdy", "g_dxdn", "st_xout", "s_rdy", "A_dn", "iter_dn", "epi_dn"]
 print("cycles relative to the first load issue (CTA 0)")
 print("  k " + " ".join("%8s" % n for n in names))
 for k in range(64):
-    if int(t[k, 9]) == 0 or k > 7:
+    if int(t[k, 9]) == 0 or k > int(os.environ.get('TRACE_ROWS', '7')):
         break
     print("%3d " % k + " ".join("%8d" % (int(t[k, e]) - base if int(t[k, e]) else -1) for e in range(13)))
+    if os.environ.get("TRACE_GRAD"):
+        print("      grad: wrdy %d copy_done %d xfull %d | " % tuple(int(t[k, e]) - base for e in (6, 25, 26)) +
+              " | ".join("c%d wait %d full %d done %d" % (c, int(t[k, 13 + c]) - base, int(t[k, 17 + c]) - base, int(t[k, 21 + c]) - base) for c in range(4)) +
+              " | dx_done %d" % (int(t[k, 7]) - base))
