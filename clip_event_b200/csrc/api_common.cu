@@ -30,6 +30,10 @@ static thread_local int g_dev_checked = -1;  // device ordinal that passed the c
 static thread_local int g_sms = 0;
 
 int check_device() {
+  // PyTorch runs backward() on its own thread: the driver entry points used for tensor maps need the
+  // primary context bound to THAT thread, which only a runtime call that touches the device does
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) {

@@ -28,7 +28,59 @@ constexpr float kLn2 = 0.6931471805599453f;
 // ------------------------------------------------------------------------------------------
 // Epilogues
 // ------------------------------------------------------------------------------------------
-template <int BN>
+// Forward-stored exponentials (bf16 mode, over-batch): while the base-2 temperature kk = s*log2(e) is at most
+// 40 every scaled logit lies in [-kk, kk], so the forward epilogue can use the fixed reference kk and store
+//   E[r,c] = 2^(v[r,c] - kk) / |col c|
+// next to the row statistics.  The backward then needs no recompute GEMM: with rho_r = coef 2^(kk - lse_r) / |row r|
+//   G = diag(rho) E + coef (p_lab - 1) * one-hot / (|row||col|)      (E has a hole at the positive's column),
+// i.e. the gradient GEMMs run on E with rho folded into a row scale (G B) or into the rows of the other
+// operand (G^t B), and the positive's column is a sparse fp32 correction.  The switch is taken ON THE DEVICE from
+// logit_scale (no host read, graph-capturable): at higher temperatures (a CLIP checkpoint has s = 100) the
+// row maximum is only known after the forward pass, nothing is stored and the recompute path runs.
+__device__ __forceinline__ bool stored_exp_on(const float* logit_scale) {
+  return expf(__ldg(logit_scale)) * kLog2e <= 40.f;
+}
+
+// 32 columns of this thread's row -> bf16 -> the warp's 128-byte-swizzled [32 x 64] staging box; every second
+// chunk hands the box to the TMA (box row = tile row of lane 0).  Measured alternatives (tools/gemm_trace.py,
+// cycles per 128 x 256 tile, main loop alone = 5300): thread-per-row global stores 9800 (32 half-filled
+// sectors per instruction); a box per warp-tile 4000 but its 64 KB cost the main loop its fourth stage
+// (TMA-latency bound, 7200 per tile); a box per chunk 5700 (fence + store issue four times per tile).
+__device__ __forceinline__ void stage_chunk_bf16(const float* gs, uint8_t* stage, const CUtensorMap* out_map,
+                                                 int lcol0, int col0, int row, int64_t ldg) {
+  const int lane = threadIdx.x & 31;
+  const int odd = (lcol0 >> 5) & 1;
+  if (!odd) {
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+  }
+  uint8_t* rowp = stage + lane * 128;
+  const int sw = lane & 7;
+  const int slot0 = odd * 4;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    uint4 pk;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(gs[i], gs[i + 1]);
+    __nv_bfloat162 t1 = __floats2bfloat162_rn(gs[i + 2], gs[i + 3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(gs[i + 4], gs[i + 5]);
+    __nv_bfloat162 t3 = __floats2bfloat162_rn(gs[i + 6], gs[i + 7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&t0);
+    pk.y = *reinterpret_cast<uint32_t*>(&t1);
+    pk.z = *reinterpret_cast<uint32_t*>(&t2);
+    pk.w = *reinterpret_cast<uint32_t*>(&t3);
+    *reinterpret_cast<uint4*>(rowp + (((slot0 + i / 8) ^ sw) << 4)) = pk;
+  }
+  if (odd) {
+    fence_proxy_async();   // generic-proxy writes of the box -> visible to the TMA (async proxy)
+    __syncwarp();
+    if (lane == 0 && col0 - 32 < (int)ldg) {
+      tma_store_2d(out_map, stage, col0 - 32, row);   // lane 0's row is the first row of the box
+      tma_store_commit();
+    }
+  }
+}
+
+template <int BN, bool STORE = false>
 struct EpiStats {
   struct Params {
     const float* rinv_row;
@@ -39,12 +91,18 @@ struct EpiStats {
     const int* lab;     // [M] column of the row's positive (or -1)
     float* lab_logit;   // [M] natural-log logit at that column, taken from the SAME accumulator so
                         //     that the tensor-core rounding cancels in (LSE - positive logit)
+    int64_t lde;        // STORE: row pitch (elements) of the bf16 E matrix behind out_map
   };
-  static constexpr int kStageBytesPerWarp = 0;
+  static constexpr int kStageBytesPerWarp = STORE ? 32 * 128 : 0;
   uint8_t* stage;
   const CUtensorMap* out_map;
   Params p;
-  __device__ __forceinline__ void finish() {}
+  static __device__ __forceinline__ bool skip_all(const Params&) { return false; }
+  __device__ __forceinline__ void finish() {
+    if constexpr (STORE) {
+      if ((threadIdx.x & 31) == 0) tma_store_wait_all();
+    }
+  }
   float kk, rinv_r, m2, l;
   int lab;
   bool fixed_ref;
@@ -80,6 +138,50 @@ struct EpiStats {
 #pragma unroll
       for (int i = 0; i < 32; ++i) pick = (col0 + i == lab) ? acc[i] * (ks * s_epi[lcol0 + i]) : pick;
       p.lab_logit[row] = pick * kLn2;
+    }
+    if constexpr (STORE) {
+      if (fixed_ref) {   // warp-uniform: the exponentials double as the stored E = 2^(v - kk) / |col|
+        float gs[32];
+        if (full) {   // packed f32x2 arithmetic (the FMA pipe issues one warp instruction every two cycles)
+          const float4* rc4 = reinterpret_cast<const float4*>(s_epi + lcol0);
+          const float2 ks2 = make_float2(ks, ks), nk2 = make_float2(-kk, -kk);
+          float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 r4 = rc4[i4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = 4 * i4 + 2 * h;
+              const float2 rc2 = h == 0 ? make_float2(r4.x, r4.y) : make_float2(r4.z, r4.w);
+              const float2 v2 = __ffma2_rn(make_float2(acc[i], acc[i + 1]), __fmul2_rn(ks2, rc2), nk2);
+              const float2 e2 = make_float2(ex2(v2.x), ex2(v2.y));
+              sum2 = __fadd2_rn(sum2, e2);
+              const float2 o2 = __fmul2_rn(e2, rc2);
+              gs[i] = o2.x;
+              gs[i + 1] = o2.y;
+            }
+          }
+          l += sum2.x + sum2.y;
+        } else {
+          float s0 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float rc0 = s_epi[lcol0 + i];
+            const float e0 = (col0 + i < p.N) ? ex2(fmaf(acc[i], ks * rc0, -kk)) : 0.f;
+            s0 += e0;
+            gs[i] = e0 * rc0;
+          }
+          l += s0;
+        }
+        // the positive's entry is left out of E: softmax - 1 at that column would cancel in bf16 once the
+        // model is trained (p -> 1); the backward adds coef (p - 1) there in fp32 (bwd_onehot_kernel)
+        if ((unsigned)(lab - col0) < 32u) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) gs[i] = (col0 + i == lab) ? 0.f : gs[i];
+        }
+        stage_chunk_bf16(gs, stage, out_map, lcol0, col0, row, p.lde);
+        return;
+      }
     }
     if (fixed_ref && full) {
       float s0 = 0.f, s1 = 0.f;
@@ -130,8 +232,10 @@ struct EpiGrad {
     int64_t ldg;
     float* dls_part;         // [tiles, 8]
     int M, N;
+    int stored;              // the forward may have stored E (stored_exp_on decides on the device): nothing to do then
   };
   Params p;
+  static __device__ __forceinline__ bool skip_all(const Params& q) { return q.stored != 0 && stored_exp_on(q.logit_scale); }
   // Per element: t = kr*rc ; v = acc*t - lse (base-2 log-probability) ; g' = cs * 2^v ;
   // G = g' * t ; dls' += g' * v.   Here kr = s*log2e/|row|, cs = coef/(s*log2e), so that
   // g'*t = coef*softmax/(|row||col|) and sum(g*L) = s*log2e*ln2 * sum(g'*(v + lse)); the lse part
@@ -225,39 +329,7 @@ struct EpiGrad {
       }
     }
     if constexpr (!TF32X3) {
-      // the box row is 128 bytes = eight 16-byte slots, XOR-swizzled with the row as SWIZZLE_128B
-      // expects; even chunks fill slots 0..3 (after the previous store has drained the box), odd
-      // chunks slots 4..7 and hand the box to the TMA
-      const int lane = threadIdx.x & 31;
-      const int odd = (lcol0 >> 5) & 1;
-      if (!odd) {
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
-      }
-      uint8_t* rowp = stage + lane * 128;
-      const int sw = lane & 7;
-      const int slot0 = odd * 4;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 pk;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(gs[i], gs[i + 1]);
-        __nv_bfloat162 t1 = __floats2bfloat162_rn(gs[i + 2], gs[i + 3]);
-        __nv_bfloat162 t2 = __floats2bfloat162_rn(gs[i + 4], gs[i + 5]);
-        __nv_bfloat162 t3 = __floats2bfloat162_rn(gs[i + 6], gs[i + 7]);
-        pk.x = *reinterpret_cast<uint32_t*>(&t0);
-        pk.y = *reinterpret_cast<uint32_t*>(&t1);
-        pk.z = *reinterpret_cast<uint32_t*>(&t2);
-        pk.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(rowp + (((slot0 + i / 8) ^ sw) << 4)) = pk;
-      }
-      if (odd) {
-        fence_proxy_async();   // generic-proxy writes of the box -> visible to the TMA (async proxy)
-        __syncwarp();
-        if (lane == 0 && col0 - 32 < (int)p.ldg) {
-          tma_store_2d(out_map, stage, col0 - 32, row);   // lane 0's row is the first row of the box
-          tma_store_commit();
-        }
-      }
+      stage_chunk_bf16(gs, stage, out_map, lcol0, col0, row, p.ldg);
       return;
     }
     if (!ok) return;
@@ -299,6 +371,7 @@ struct EpiStore {
     int atomic;                // 1: accumulate with red.add (split-K); 2: exclusive tile, out += v
     int M, N;
   };
+  static __device__ __forceinline__ bool skip_all(const Params&) { return false; }
   static constexpr int kStageBytesPerWarp = 0;
   uint8_t* stage;
   const CUtensorMap* out_map;
@@ -858,6 +931,138 @@ int launch_normalize_bwd(const void* x, const float* d, int rows, int D, void* o
 }
 
 // ------------------------------------------------------------------------------------------
+// Stored-exponentials backward (see stored_exp_on): row scales, the one-hot corrections and dlogit_scale
+// ------------------------------------------------------------------------------------------
+struct BwdPrepArgs {
+  const void* img; const void* pos; const float* ls;
+  const float *g_i, *g_t;
+  float inv_Ri, inv_Pt;
+  const float *lse2_row, *lse2_col, *rinv_i, *norm_i, *rinv_p, *norm_p;
+  float *rs_i, *rs_p;
+  void *img_s, *pos_s;
+  int R, P, D;
+};
+// One warp per row (images | positives): rho = coef 2^(kk - lse) / |row|, row scale |row| rho, scaled bf16 copy
+// of the row.  On the recompute path (temperature too high for stored exponentials) the scales are |row| and
+// the copies are plain, so that the gradient GEMMs that follow are the same launches on either path.
+__global__ void bwd_prep_kernel(BwdPrepArgs a) {
+  const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wi >= a.R + a.P) return;
+  const bool is_img = wi < a.R;
+  const int r = is_img ? wi : wi - a.R;
+  const float kk = expf(__ldg(a.ls)) * kLog2e;
+  const bool on = kk <= 40.f;
+  float rho = 1.f, rs;
+  if (is_img) {
+    if (on) rho = __ldg(a.g_i) * a.inv_Ri * ex2(kk - a.lse2_row[r]) * a.rinv_i[r];
+    rs = a.norm_i[r] * rho;
+    if (lane == 0) a.rs_i[r] = rs;
+  } else {
+    if (on) rho = __ldg(a.g_t) * a.inv_Pt * ex2(kk - a.lse2_col[r]) * a.rinv_p[r];
+    rs = a.norm_p[r] * rho;
+    if (lane == 0) a.rs_p[r] = rs;
+  }
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(is_img ? a.img : a.pos) + (int64_t)r * a.D;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(is_img ? a.img_s : a.pos_s) + (int64_t)r * a.D;
+  for (int c = lane * 8; c < a.D; c += 256) {
+    float v[8];
+    In<CE_BF16>::load16(x + c, v);
+    uint4 pk;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0] * rho, v[1] * rho), t1 = __floats2bfloat162_rn(v[2] * rho, v[3] * rho);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4] * rho, v[5] * rho), t3 = __floats2bfloat162_rn(v[6] * rho, v[7] * rho);
+    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+    *reinterpret_cast<uint4*>(o + c) = pk;
+  }
+}
+
+struct BwdFixArgs {
+  const void* img; const void* txt; const void* pos; const float* ls;
+  const float *g_i, *g_t;
+  float inv_Ri, inv_Pt;
+  const float *rinv_i, *rinv_t, *rinv_p;
+  const int *lab_local, *lab_t;
+  const float *lab_logit_i, *lab_logit_t, *lse2_row, *lse2_col;
+  float *dimg_hat, *dtxt_hat, *dpos_hat;
+  int R, P, D;
+};
+// The positive's column of G (and of Gt), which the E matrices leave out: with q = coef (p_lab - 1), p_lab from
+// the forward's fp32 label logit and row LSE (expm1: exact where a trained model has p -> 1),
+//   image r, local positive column c:  dI^[r] += s q t^[c],  dT^[c] += s q i^[r];
+//   positive p of image r:             dT^pos[p] += s q_t i^[r],  dI^[r] += s q_t t^pos[p].
+// One warp per item, red.add (rows can repeat).
+// Two launches (side 0: images, side 1: positives): both add into dI^ rows, and a fixed order between the two keeps
+// the result reproducible run to run (within a side a row has one contributor unless labels repeat).
+__global__ void bwd_onehot_kernel(BwdFixArgs a, int side) {
+  if (!stored_exp_on(a.ls)) return;
+  const int lane = threadIdx.x & 31;
+  const int wi = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + (side ? a.R : 0);
+  if (wi >= (side ? a.R + a.P : a.R)) return;
+  const float s = expf(__ldg(a.ls));
+  const __nv_bfloat16 *xa, *xb;
+  float *da, *db;
+  float ca, cb;
+  if (wi < a.R) {
+    const int r = wi, c = a.lab_local[r];
+    if (c < 0) return;
+    const float k = s * __ldg(a.g_i) * a.inv_Ri * expm1f(a.lab_logit_i[r] - a.lse2_row[r] * kLn2);
+    xa = reinterpret_cast<const __nv_bfloat16*>(a.txt) + (int64_t)c * a.D; ca = k * a.rinv_t[c]; da = a.dimg_hat + (int64_t)r * a.D;
+    xb = reinterpret_cast<const __nv_bfloat16*>(a.img) + (int64_t)r * a.D; cb = k * a.rinv_i[r]; db = a.dtxt_hat + (int64_t)c * a.D;
+  } else {
+    const int p = wi - a.R, r = a.lab_t[p];
+    if (r < 0) return;
+    const float k = s * __ldg(a.g_t) * a.inv_Pt * expm1f(a.lab_logit_t[p] - a.lse2_col[p] * kLn2);
+    xa = reinterpret_cast<const __nv_bfloat16*>(a.img) + (int64_t)r * a.D; ca = k * a.rinv_i[r]; da = a.dpos_hat + (int64_t)p * a.D;
+    xb = reinterpret_cast<const __nv_bfloat16*>(a.pos) + (int64_t)p * a.D; cb = k * a.rinv_p[p]; db = a.dimg_hat + (int64_t)r * a.D;
+  }
+  for (int c0 = lane * 8; c0 < a.D; c0 += 256) {
+    float u[8], v[8];
+    In<CE_BF16>::load16(xa + c0, u);
+    In<CE_BF16>::load16(xb + c0, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { atomicAdd(da + c0 + i, ca * u[i]); atomicAdd(db + c0 + i, cb * v[i]); }
+  }
+}
+
+// dlogit_scale = sum_r <dL/dI^[r], I^[r]> (every logit is s I^ . T^, so sum G (.) L over a row is that dot):
+// block partials in base-2 units (the chain's last kernel sums them and multiplies by ln 2).
+__global__ void __launch_bounds__(256) bwd_dls_dot_kernel(const void* img, const float* rinv_i, const float* dimg_hat,
+                                                          const float* ls, int R, int D, float* part) {
+  __shared__ float sh[8];
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  float dot = 0.f;
+  if (r < R && stored_exp_on(ls)) {
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(img) + (int64_t)r * D;
+    const float* d = dimg_hat + (int64_t)r * D;
+    for (int c = lane * 8; c < D; c += 256) {
+      float v[8];
+      In<CE_BF16>::load16(x + c, v);
+      const float4 d0 = *reinterpret_cast<const float4*>(d + c), d1 = *reinterpret_cast<const float4*>(d + c + 4);
+      dot += v[0] * d0.x + v[1] * d0.y + v[2] * d0.z + v[3] * d0.w + v[4] * d1.x + v[5] * d1.y + v[6] * d1.z + v[7] * d1.w;
+    }
+    dot = warp_sum(dot) * rinv_i[r];
+  }
+  if (lane == 0) sh[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    part[blockIdx.x] = t / kLn2;
+  }
+}
+
+// Host-side gate (the same decision in forward and backward).  Measured (bf16, one B200): 4096 x 36864 logits
+// 607 -> 559 us per forward + backward; 1024 x 9216 176 -> 186 us and 256 x 2304 92 -> 104 us (the saved recompute
+// GEMM no longer outweighs the extra launches and the store), so small problems keep the recompute path.
+// CE_CTR_STORED=0 / 2 (tuning aid) forces the path off / on.
+inline bool stored_exp_enabled(int R, int C) {
+  static const int mode = [] { const char* e = getenv("CE_CTR_STORED"); return e == nullptr ? 1 : atoi(e); }();
+  if (mode == 0) return false;
+  if (mode == 2) return true;
+  return (int64_t)R * C >= (int64_t)1 << 25;
+}
+
+// ------------------------------------------------------------------------------------------
 // workspace
 // ------------------------------------------------------------------------------------------
 struct CtrWs {
@@ -873,6 +1078,8 @@ struct CtrWs {
   void* G[2];      // image-side gradient matrix [R, ldg]
   void* Gt[2];     // text-side  gradient matrix [P, ldgt]
   float *dtxt_hat, *dimg_hat, *dpos_hat, *logits_bt;
+  void *img_s, *pos_s;   // bf16: image / positive rows scaled by rho (stored-exponentials backward)
+  float *rs_i, *rs_p;    // row scales of the gradient GEMMs: |row| * rho (or |row| on the recompute path)
   int64_t ldg, ldgt;
   int nblk_i, nblk_t, tiles_g, tiles_gt;
   size_t bytes;
@@ -916,6 +1123,10 @@ CtrWs carve(void* base, int R, int C, int P, int D, int dtype) {
     w.Gt[1] = cv.take<float>((size_t)P * w.ldgt);
   } else {
     w.pos_p[0] = cv.take<__nv_bfloat16>((size_t)P * D);
+    w.img_s = cv.take<__nv_bfloat16>((size_t)R * D);
+    w.pos_s = cv.take<__nv_bfloat16>((size_t)P * D);
+    w.rs_i = cv.take<float>(R);
+    w.rs_p = cv.take<float>(P);
     w.ldg = (C + 7) / 8 * 8;
     w.ldgt = (R + 7) / 8 * 8;
     w.G[0] = cv.take<__nv_bfloat16>((size_t)R * w.ldg);
@@ -1005,9 +1216,21 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
   GemmOperand oi = operand<DT>(img, w.img_p, R, D, 0);
   GemmOperand ot = operand<DT>(txt, w.txt_p, C, D, 0);
   GemmOperand op = operand<DT>(w.pos_p[0], w.pos_p, P, D, 0);
+  bool store = false;
+  if constexpr (!TF) store = stored_exp_enabled(R, C) && mode == 0;
   if (mode == 0) {
-    typename EpiStats<BN>::Params ep{w.rinv_i, w.rinv_t, ls, w.part_i, R, C, w.nblk_i, w.lab_local, w.lab_logit_i};
-    CE_TRY((launch_gemm_auto<TF, BN, EpiStats<BN>>(1, oi, ot, D, ep, st)));
+    typename EpiStats<BN>::Params ep{w.rinv_i, w.rinv_t, ls, w.part_i, R, C, w.nblk_i, w.lab_local, w.lab_logit_i, w.ldg};
+    if constexpr (!TF) {
+      if (store) {
+        const GemmOut go{w.G[0], R, (int)w.ldg, w.ldg};
+        typename EpiStats<BN, true>::Params eps{w.rinv_i, w.rinv_t, ls, w.part_i, R, C, w.nblk_i, w.lab_local, w.lab_logit_i, w.ldg};
+        CE_TRY((launch_gemm_auto<TF, BN, EpiStats<BN, true>>(1, oi, ot, D, eps, st, &go)));
+      } else {
+        CE_TRY((launch_gemm_auto<TF, BN, EpiStats<BN>>(1, oi, ot, D, ep, st)));
+      }
+    } else {
+      CE_TRY((launch_gemm_auto<TF, BN, EpiStats<BN>>(1, oi, ot, D, ep, st)));
+    }
   } else {
     InstArgs ia{};
     ia.img = img; ia.txt = txt; ia.logit_scale = ls; ia.labels = labels_i_v; ia.rinv_i = w.rinv_i;
@@ -1017,8 +1240,18 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     CE_LAUNCH_CHECK();
   }
   {
-    typename EpiStats<BN>::Params ep{w.rinv_p, w.rinv_i, ls, w.part_t, P, R, w.nblk_t, w.lab_t, w.lab_logit_t};
-    CE_TRY((launch_gemm_auto<TF, BN, EpiStats<BN>>(1, op, oi, D, ep, st)));
+    typename EpiStats<BN>::Params ep{w.rinv_p, w.rinv_i, ls, w.part_t, P, R, w.nblk_t, w.lab_t, w.lab_logit_t, w.ldgt};
+    if constexpr (!TF) {
+      if (store) {
+        const GemmOut go{w.Gt[0], P, (int)w.ldgt, w.ldgt};
+        typename EpiStats<BN, true>::Params eps{w.rinv_p, w.rinv_i, ls, w.part_t, P, R, w.nblk_t, w.lab_t, w.lab_logit_t, w.ldgt};
+        CE_TRY((launch_gemm_auto<TF, BN, EpiStats<BN, true>>(1, op, oi, D, eps, st, &go)));
+      } else {
+        CE_TRY((launch_gemm_auto<TF, BN, EpiStats<BN>>(1, op, oi, D, ep, st)));
+      }
+    } else {
+      CE_TRY((launch_gemm_auto<TF, BN, EpiStats<BN>>(1, op, oi, D, ep, st)));
+    }
   }
   // (max, sum) merge of the per-tile statistics, the positives' slots, the text-side sum and -- on one
   // GPU (loss_i != nullptr) -- both losses and the row LSE: one launch
@@ -1085,12 +1318,32 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
   GemmOperand oi = operand<DT>(img, w.img_p, R, D, 0);
   GemmOperand ot = operand<DT>(txt, w.txt_p, C, D, 0);
   GemmOperand op = operand<DT>(w.pos_p[0], w.pos_p, P, D, 0);
-  const int n_dls = (w.tiles_g + w.tiles_gt) * 8 + (mode == 0 ? 0 : C / T);
+  bool stored = false;
+  if constexpr (!TF) stored = stored_exp_enabled(R, C) && mode == 0;
+  const int dot_blocks = stored ? (R * 32 + 255) / 256 : 0;
+  const int n_dls = (w.tiles_g + w.tiles_gt) * 8 + (mode == 0 ? dot_blocks : C / T);
+  const float* rs_i = w.norm_i;
+  const float* rs_p = w.norm_p;
+  const void* img_b = img;              // B operand of G^t img
+  const void* pos_b = w.pos_p[0];       // B operand of Gt^t pos
+  if (stored) {
+    // the gradient epilogues return at once when the forward stored E: their partials must read as zero
+    CE_CUDA_TRY(cudaMemsetAsync(w.dls_part, 0, sizeof(float) * (size_t)(w.tiles_g + w.tiles_gt) * 8, st));
+    BwdPrepArgs pa{};
+    pa.img = img; pa.pos = w.pos_p[0]; pa.ls = ls; pa.g_i = g_i; pa.g_t = g_t;
+    pa.inv_Ri = 1.f / (float)R_total; pa.inv_Pt = 1.f / (float)P_total;
+    pa.lse2_row = w.lse2_row; pa.lse2_col = w.lse2_col; pa.rinv_i = w.rinv_i; pa.norm_i = w.norm_i;
+    pa.rinv_p = w.rinv_p; pa.norm_p = w.norm_p; pa.rs_i = w.rs_i; pa.rs_p = w.rs_p;
+    pa.img_s = w.img_s; pa.pos_s = w.pos_s; pa.R = R; pa.P = P; pa.D = D;
+    bwd_prep_kernel<<<((R + P) * 32 + 255) / 256, 256, 0, st>>>(pa);
+    CE_LAUNCH_CHECK();
+    rs_i = w.rs_i; rs_p = w.rs_p; img_b = w.img_s; pos_b = w.pos_s;
+  }
   if (mode == 0) {  // image side: rows = images, columns = local descriptions
     typename EpiGrad<BN, TF>::Params ep{};
     ep.rinv_row = w.rinv_i; ep.rinv_col = w.rinv_t; ep.logit_scale = ls; ep.lse2_row = w.lse2_row;
     ep.lab_row = w.lab_local; ep.g = g_i; ep.inv_count = 1.f / (float)R_total;
-    ep.G0 = w.G[0]; ep.G1 = w.G[1]; ep.ldg = w.ldg; ep.dls_part = w.dls_part; ep.M = R; ep.N = C;
+    ep.G0 = w.G[0]; ep.G1 = w.G[1]; ep.ldg = w.ldg; ep.dls_part = w.dls_part; ep.M = R; ep.N = C; ep.stored = stored ? 1 : 0;
     const GemmOut go{w.G[0], R, (int)w.ldg, w.ldg};
     CE_TRY((launch_gemm_auto<TF, BN, EpiGrad<BN, TF>>(2, oi, ot, D, ep, st, TF ? nullptr : &go)));
   } else {          // over-instance image side: direct kernel, writes d I^ (local rows) and d T^
@@ -1110,21 +1363,38 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     ep.rinv_row = w.rinv_p; ep.rinv_col = w.rinv_i; ep.logit_scale = ls; ep.lse2_row = w.lse2_col;
     ep.lab_row = w.lab_t; ep.g = g_t; ep.inv_count = 1.f / (float)P_total;
     ep.G0 = w.Gt[0]; ep.G1 = w.Gt[1]; ep.ldg = w.ldgt; ep.dls_part = w.dls_part + (size_t)w.tiles_g * 8;
-    ep.M = P; ep.N = R;
+    ep.M = P; ep.N = R; ep.stored = stored ? 1 : 0;
     const GemmOut go{w.Gt[0], P, (int)w.ldgt, w.ldgt};
     CE_TRY((launch_gemm_auto<TF, BN, EpiGrad<BN, TF>>(2, op, oi, D, ep, st, TF ? nullptr : &go)));
   }
+  // With stored exponentials G = diag(rho) E - one-hot: rho rides on the row scale where G is the left operand
+  // with its rows, and on the rows of the other operand where G enters transposed.
   GemmOperand tB = operand<DT>(txt, w.txt_p, D, D, 1);          // [K = C, N = D]
   GemmOperand iB = operand<DT>(img, w.img_p, D, D, 1);          // [K = R, N = D]
-  GemmOperand pB = operand<DT>(w.pos_p[0], w.pos_p, D, D, 1);   // [K = P, N = D]
+  GemmOperand iBs = operand<DT>(img_b, w.img_p, D, D, 1);       // the same, rows scaled by rho (stored path)
+  GemmOperand pBs = operand<DT>(pos_b, w.pos_p, D, D, 1);       // [K = P, N = D]
   // d I^ (partial over the local columns) = s |i| (G txt + Gt^t pos)
   if (mode == 0)
-    CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, R, w.ldg, 0), tB, C, dimg_hat_part, D, w.norm_i, ls, false, st)));
-  CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, R, w.ldgt, 1), pB, P, dimg_hat_part, D, w.norm_i, ls, true, st)));
+    CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, R, w.ldg, 0), tB, C, dimg_hat_part, D, rs_i, ls, false, st)));
+  CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, R, w.ldgt, 1), pBs, P, dimg_hat_part, D, w.norm_i, ls, true, st)));
   // d T^ = s |t| G^t img  (+ s |t_pos| Gt img on the positive rows, added by the row kernel)
   if (mode == 0)
-    CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, C, w.ldg, 1), iB, R, w.dtxt_hat, D, w.norm_t, ls, false, st)));
-  CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, P, w.ldgt, 0), iB, R, w.dpos_hat, D, w.norm_p, ls, false, st)));
+    CE_TRY((plain_gemm<TF>(operand<DT>(w.G[0], w.G, C, w.ldg, 1), iBs, R, w.dtxt_hat, D, w.norm_t, ls, false, st)));
+  CE_TRY((plain_gemm<TF>(operand<DT>(w.Gt[0], w.Gt, P, w.ldgt, 0), iB, R, w.dpos_hat, D, rs_p, ls, false, st)));
+  if (stored) {
+    BwdFixArgs fa{};
+    fa.img = img; fa.txt = txt; fa.pos = w.pos_p[0]; fa.ls = ls; fa.g_i = g_i; fa.g_t = g_t;
+    fa.inv_Ri = 1.f / (float)R_total; fa.inv_Pt = 1.f / (float)P_total;
+    fa.rinv_i = w.rinv_i; fa.rinv_t = w.rinv_t; fa.rinv_p = w.rinv_p; fa.lab_local = w.lab_local; fa.lab_t = w.lab_t;
+    fa.lab_logit_i = w.lab_logit_i; fa.lab_logit_t = w.lab_logit_t; fa.lse2_row = w.lse2_row; fa.lse2_col = w.lse2_col;
+    fa.dimg_hat = dimg_hat_part; fa.dtxt_hat = w.dtxt_hat; fa.dpos_hat = w.dpos_hat; fa.R = R; fa.P = P; fa.D = D;
+    bwd_onehot_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(fa, 0);
+    bwd_onehot_kernel<<<(P * 32 + 255) / 256, 256, 0, st>>>(fa, 1);
+    CE_LAUNCH_CHECK();
+    bwd_dls_dot_kernel<<<dot_blocks, 256, 0, st>>>(img, w.rinv_i, dimg_hat_part, ls, R, D,
+                                                   w.dls_part + (size_t)(w.tiles_g + w.tiles_gt) * 8);
+    CE_LAUNCH_CHECK();
+  }
   CE_TRY((launch_normalize_bwd<DT>(txt, w.dtxt_hat, C, D, dtxt, w.col_pos, w.dpos_hat, st, w.dls_part, n_dls, dls_out)));
   return CE_OK;
 }

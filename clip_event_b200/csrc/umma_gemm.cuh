@@ -128,6 +128,7 @@ struct TileWalk {
 //                int lcol0 /*tile-local column*/, const float* s_epi, int row, bool row_ok);
 //     void row_end(int row, bool row_ok, int m_blk, int n_blk, int k_split, float* s_epi, int et, int half);
 //     void finish();                                // once, after the last tile
+//     static bool skip_all(const Params&);          // true (for the whole grid): the kernel returns at once
 //   };
 
 template <bool TF32X3, int BN, class Epi, int CG = 1>
@@ -136,6 +137,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
   using Cfg = GemmCfg<TF32X3, BN, Epi::kStageBytesPerWarp * 8, CG>;
   // plain pointer arithmetic on the shared array keeps the address space known to the compiler
   // (LDS/STS instead of generic LD/ST in the epilogues)
+  if (Epi::skip_all(ep)) return;   // device-side switch between two paths of a captured launch sequence (grid-uniform)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // swizzled TMA / UMMA tiles need 1024-byte alignment
   uint8_t* stage_base = smem;

@@ -472,8 +472,9 @@ def test_integration_md_ctypes_stubs_run():
                                                              lpi.cuda(), lpt.cuda(), idx.cuda())
         torch.cuda.synchronize()
         assert a.item() == li and b.item() == lt
-        # split-K partial sums meet in red.add, so gradients repeat to rounding, not bit for bit
-        assert rel_err(gi, dimg) < 1e-5 and rel_err(gt, dtxt) < 1e-5 and close(gl.item(), dls, 1e-5, 1e-7)
+        # split-K partial sums meet in red.add, so gradients repeat to rounding, not bit for bit (a few bf16
+        # elements per 10^5 flip by one unit in the last place between two runs)
+        assert rel_err(gi, dimg) < 1e-4 and rel_err(gt, dtxt) < 1e-4 and close(gl.item(), dls, 1e-5, 1e-7)
         etxt, obj, tnum, onum = syn.ot_inputs(32, w.M, w.N, w.D, 6, "ragged", dtype=dtype)
         loss, dist, dt_, do_ = run_ot(etxt, obj, tnum, onum)
         l2, d2, dt2, do2 = ns["ot_loss_and_grads"](etxt.cuda(), obj.cuda(), tnum.cuda(), onum.cuda())

@@ -253,6 +253,23 @@ def test_fused_ot_kernel_parity():
 
 
 # ------------------------------------------------------------------------------------------
+# forward-stored exponentials (csrc/contrastive.cu, stored_exp_on): the backward without a recompute GEMM is
+# gated to large problems by default; CE_CTR_STORED=2 forces it so that every small parity case (goldens,
+# oracle comparisons, ragged edges, arbitrary labels, the temperature-100 cases that fall back on the device)
+# runs through it in a fresh process
+# ------------------------------------------------------------------------------------------
+def test_contrastive_parity_with_stored_exponentials_forced():
+    env = dict(os.environ, CE_CTR_STORED="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-k",
+                        "contrastive or golden or engine_style or temperature or loss_head_step",
+                        os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_gpu_round2.py"),
+                        "--deselect", "tests/test_gpu_round2.py::test_contrastive_parity_with_stored_exponentials_forced"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:]
+
+
+# ------------------------------------------------------------------------------------------
 # engine.py:89-90 on the head's own parameter: clip_grad_norm_ + optimizer.step() in one launch
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["sgd", "adam"])
