@@ -22,6 +22,11 @@ struct OtFusedArgs {
   void* dtxt;                 // nullable (forward only): same layout as txt
   void* dimg;                 // same layout as img
   void* dslot0;               // nullable: [B] rows of D elements, stride img_bs, zero-filled
+  // stream kernel only -- packed (variable-length) node layout: rows of sample b are txt_off[b] .. txt_off[b+1]-1 of a
+  // dense [sum_m, D] matrix (likewise img_off); every row is a valid node, M / N are the maxima over the batch,
+  // masks and sample strides are ignored and gradients come back in the same packed layout
+  const int* txt_off;
+  const int* img_off;
   int slots;                  // filled in by the launcher (fused: resident slots; stream: parks)
   int cy_depth, gy_depth;     // stream kernel: chunk ring depths of the cost / gradient stage
   int poll_mode;              // debug (CE_OT_POLL)

@@ -1427,6 +1427,36 @@ extern "C" int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* i
   return CE_OK;
 }
 
+// Packed (variable-length) node sets: SURVEY.md 8f-3 -- the padded slots of model_clip.py:531-552 /
+// dataset_voa.py:532-544,566-577 never reach the kernel.  Served by the streaming kernel only.
+extern "C" int ce_ot_fwd_bwd_packed(const void* txt_rows, const int32_t* txt_off, const void* img_rows,
+                                    const int32_t* img_off, int B, int max_m, int max_n, int D, int dtype,
+                                    float beta, int iters, int k, float loss_scale, float* dist, float* loss,
+                                    void* dtxt_rows, void* dimg_rows, ce_stream_t stream) {
+  CE_TRY(check_device());
+  if (dtype != CE_BF16) return fail(CE_ERR_DTYPE, "packed OT: bf16 only (pad the node sets for fp32)");
+  if (B < 0 || iters < 0 || k < 1 || !(beta > 0.f)) return fail(CE_ERR_ARG, "packed OT: bad B / iters / k / beta");
+  if (!ot_stream_supported(max_m, max_n, D, dtype))
+    return fail(CE_ERR_SHAPE, "packed OT: needs max_m <= 16, max_n <= 64 and D a multiple of 64 up to 512 (max_m=%d max_n=%d D=%d); pad the node sets instead", max_m, max_n, D);
+  if ((dtxt_rows == nullptr) != (dimg_rows == nullptr)) return fail(CE_ERR_ARG, "packed OT: pass both gradient buffers or neither");
+  if (((uintptr_t)txt_rows | (uintptr_t)img_rows | (uintptr_t)dtxt_rows | (uintptr_t)dimg_rows) & 15)
+    return fail(CE_ERR_ALIGN, "packed OT: row matrices must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (B == 0) {
+    if (loss) CE_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    return CE_OK;
+  }
+  OtFusedArgs fa{};
+  fa.txt = txt_rows; fa.img = img_rows; fa.txt_off = txt_off; fa.img_off = img_off;
+  fa.B = B; fa.M = max_m; fa.N = max_n; fa.D = D;
+  fa.beta = beta; fa.eps = 1e-5f; fa.scale = loss_scale; fa.iters = iters; fa.k = k;
+  fa.dist = dist; fa.dtxt = dtxt_rows; fa.dimg = dimg_rows; fa.dslot0 = nullptr;
+  CE_TRY(launch_ot_stream(fa, st));
+  ot_tail_kernel<CE_BF16><<<1, 256, 0, st>>>(dist, B, loss_scale, loss, nullptr, 0, D);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}
+
 extern "C" int ce_ot_cost_matrix(const void* x, const void* y, int B, int M, int N, int D,
                                  int dtype, float eps, float* cost, ce_stream_t stream) {
   CE_TRY(check_device());

@@ -197,6 +197,16 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
   const int g = lane >> 2, t = lane & 3;
   const int count = (a.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool grads = a.dtxt != nullptr;
+  const bool packed = a.txt_off != nullptr;
+  // per-sample geometry: element offsets of the sample's first text / image row and its node counts
+  auto sample_geom = [&](int64_t b, int64_t& xo, int64_t& yo, int& m, int& n) {
+    if (packed) {
+      const int t0 = __ldg(a.txt_off + b), t1 = __ldg(a.txt_off + b + 1), i0 = __ldg(a.img_off + b), i1 = __ldg(a.img_off + b + 1);
+      xo = (int64_t)t0 * a.D; yo = (int64_t)i0 * a.D; m = t1 - t0; n = i1 - i0;
+    } else {
+      xo = b * a.txt_bs; yo = b * a.img_bs; m = a.M; n = a.N;
+    }
+  };
   const uint32_t sleep_ns = (uint32_t)a.poll_mode;
 
   // ---- one-time: rows that no load ever covers (beyond M / N) must read as zeros -----------------
@@ -241,16 +251,18 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
     int qs = 0, qu = 0;                              // q % R and (q / R) & 1 without the divisions
     for (int k = 0; k < count; ++k) {
       const int64_t b = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-      const uint8_t* xg = reinterpret_cast<const uint8_t*>(a.txt) + b * a.txt_bs * 2;
-      const uint8_t* yg = reinterpret_cast<const uint8_t*>(a.img) + b * a.img_bs * 2;
+      int64_t xo, yo; int m_b, n_b;
+      sample_geom(b, xo, yo, m_b, n_b);
+      const uint8_t* xg = reinterpret_cast<const uint8_t*>(a.txt) + xo * 2;
+      const uint8_t* yg = reinterpret_cast<const uint8_t*>(a.img) + yo * 2;
       const int xs = k & 1;
       role_wait(&x_empty[xs], ((k >> 1) & 1) ^ 1, lane, sleep_ns);
       if (cost_side) OT_TRACE(k, 0); else OT_TRACE(k, 1);
-      if (lane == 0) mbar_expect_tx(&x_full[xs], (uint32_t)(a.M * row_bytes));
+      if (lane == 0) mbar_expect_tx(&x_full[xs], (uint32_t)(m_b * row_bytes));
       __syncwarp();
-      if (lane < a.M) bulk_load(xb + (size_t)xs * chunk_bytes + (size_t)lane * RS, xg + (int64_t)lane * row_bytes, (uint32_t)row_bytes, &x_full[xs]);
+      if (lane < m_b) bulk_load(xb + (size_t)xs * chunk_bytes + (size_t)lane * RS, xg + (int64_t)lane * row_bytes, (uint32_t)row_bytes, &x_full[xs]);
       for (int c = 0; c < NC; ++c, ++q) {
-        const int rows = min(kCH, a.N - c * kCH);
+        const int rows = max(0, min(kCH, n_b - c * kCH));   // packed layout: a short sample's last chunks are empty
         role_wait(&y_empty[qs], qu ^ 1, lane, sleep_ns);
         if (lane == 0) mbar_expect_tx(&y_full[qs], (uint32_t)(rows * row_bytes));
         __syncwarp();
@@ -265,10 +277,12 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
     int qs = 0, qu = 0;
     for (int k = 0; k < count; ++k) {
       const int64_t b = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-      uint8_t* dxg = reinterpret_cast<uint8_t*>(a.dtxt) + b * a.txt_bs * 2;
-      uint8_t* dyg = reinterpret_cast<uint8_t*>(a.dimg) + b * a.img_bs * 2;
+      int64_t xo, yo; int m_b, n_b;
+      sample_geom(b, xo, yo, m_b, n_b);
+      uint8_t* dxg = reinterpret_cast<uint8_t*>(a.dtxt) + xo * 2;
+      uint8_t* dyg = reinterpret_cast<uint8_t*>(a.dimg) + yo * 2;
       for (int c = 0; c < NC; ++c) {
-        const int rows = min(kCH, a.N - c * kCH);
+        const int rows = max(0, min(kCH, n_b - c * kCH));
         role_wait(&bars->gy_out[qs], qu, lane, sleep_ns);
         if (lane < rows) {
           bulk_store(dyg + (int64_t)(c * kCH + lane) * row_bytes, gy + (size_t)qs * chunk_bytes + (size_t)lane * RS, (uint32_t)row_bytes);
@@ -281,12 +295,12 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
       const int xs = k & 1;
       role_wait(&bars->gx_out[xs], (k >> 1) & 1, lane, sleep_ns);
       OT_TRACE(k, 8);
-      if (lane < a.M) {
+      if (lane < m_b) {
         bulk_store(dxg + (int64_t)lane * row_bytes, gx + (size_t)xs * chunk_bytes + (size_t)lane * RS, (uint32_t)row_bytes);
         tma_store_commit();
         tma_store_wait_read();
       } else if (lane == 31 && a.dslot0 != nullptr) {   // the dropped whole-image slot's gradient is zero
-        bulk_store(reinterpret_cast<uint8_t*>(a.dslot0) + b * a.img_bs * 2, zero_row, (uint32_t)row_bytes);
+        bulk_store(reinterpret_cast<uint8_t*>(a.dslot0) + yo * 2, zero_row, (uint32_t)row_bytes);
         tma_store_commit();
         tma_store_wait_read();
       }
@@ -415,9 +429,16 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
     for (int k = park; k < count; k += P) {
       const int64_t b = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
       // masks (global loads issued before the wait so that their latency hides behind the cost phase)
-      const bool xp_l = lane >= a.M || is_pad(a.txt_mask, a.mask_kind, b * a.txt_ms + lane);
-      const bool yp0 = lane >= a.N || is_pad(a.img_mask, a.mask_kind, b * a.img_ms + lane);
-      const bool yp1 = lane + 32 >= a.N || is_pad(a.img_mask, a.mask_kind, b * a.img_ms + lane + 32);
+      bool xp_l, yp0, yp1;
+      if (packed) {   // every row of a packed sample is a valid node
+        int64_t xo, yo; int m_b, n_b;
+        sample_geom(b, xo, yo, m_b, n_b);
+        xp_l = lane >= m_b; yp0 = lane >= n_b; yp1 = lane + 32 >= n_b;
+      } else {
+        xp_l = lane >= a.M || is_pad(a.txt_mask, a.mask_kind, b * a.txt_ms + lane);
+        yp0 = lane >= a.N || is_pad(a.img_mask, a.mask_kind, b * a.img_ms + lane);
+        yp1 = lane + 32 >= a.N || is_pad(a.img_mask, a.mask_kind, b * a.img_ms + lane + 32);
+      }
       const uint32_t xpad = __ballot_sync(0xffffffffu, xp_l) | 0xffff0000u;   // bit m: text node m is padding
       const uint32_t yv0 = __ballot_sync(0xffffffffu, !yp0), yv1 = __ballot_sync(0xffffffffu, !yp1);
       const float xlen = (float)(kMP - __popc(xpad & 0xffffu));
@@ -660,6 +681,11 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
         role_arrive(&bars->scr_free[park], lane);
         continue;
       }
+      int n_b = a.N;
+      if (packed) {
+        const int64_t b = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+        n_b = __ldg(a.img_off + b + 1) - __ldg(a.img_off + b);
+      }
       // W, ax, ay move to the hand-over buffer so that the scratch goes back to the cost warps at once.  (Keeping
       // the fragments of all four chunks in registers instead needs the chunk loop unrolled: four times the code,
       // measured 8 % slower -- the kernel is sensitive to its instruction footprint.)
@@ -690,6 +716,11 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
         const float ay0 = wbuf->ay[c * 16 + g], ay1 = wbuf->ay[c * 16 + g + 8];
         if (gw == 0) OT_TRACE(k, 13 + c);
         role_wait(&bars->gy_full[qs], qu, lane, sleep_ns);
+        if (packed && c * kCH >= n_b) {   // an empty chunk of a short sample: nothing to contract, nothing to store
+          role_arrive(&bars->gy_out[qs], lane);
+          if (++qs == GY) { qs = 0; qu ^= 1; }
+          continue;
+        }
         if (gw == 0) OT_TRACE(k, 17 + c);
         const uint32_t yb = smem_u32(gy + (size_t)qs * chunk_bytes) + (uint32_t)(lrow * RS) + (uint32_t)((dc0 + lcol) * 2);
         uint32_t f0[12], f1[12];                        // y as B operand (transposed), x as B operand, y in C layout

@@ -319,6 +319,113 @@ def ot_alignment(txt_nodes, object_vec, txt_mask, object_mask, drop_slot0=True, 
 
 
 # --------------------------------------------------------------------------------------------
+# packed (variable-length) node sets: SURVEY.md 8f-3
+# --------------------------------------------------------------------------------------------
+class PackedNodes:
+    """Node embeddings of a batch without the padding: ``rows`` [sum_b count[b], D] (sample after sample, each
+    sample's valid nodes in their original order) and ``offsets`` [B+1] int32 (``rows[offsets[b]:offsets[b+1]]``
+    belongs to sample b).  ``max_count`` is a Python int so that no launch has to wait for the device."""
+
+    def __init__(self, rows, offsets, max_count):
+        self.rows, self.offsets, self.max_count = rows, offsets, int(max_count)
+
+    @property
+    def batch(self):
+        return self.offsets.numel() - 1
+
+    def to_padded(self, width=None):
+        """[B, width, D] zero-padded copy and its [B, width] int64 validity mask (the reference's layout)."""
+        B, D = self.batch, self.rows.shape[1]
+        width = self.max_count if width is None else width
+        counts = (self.offsets[1:] - self.offsets[:-1]).to(torch.int64)
+        pos = torch.arange(width, device=self.rows.device).unsqueeze(0)
+        mask = pos < counts.unsqueeze(1)
+        out = self.rows.new_zeros(B, width, D)
+        out[mask] = self.rows
+        return out, mask.to(torch.int64)
+
+
+def pack_nodes(vec, num, drop_first=False):
+    """Padded [B, S, D] embeddings + [B, S] validity mask (``*_num`` semantics: nonzero = valid, any pattern)
+    -> :class:`PackedNodes`.  ``drop_first`` removes slot 0 first (the whole-image slot, model_clip.py:686).
+    This is the converter for callers that still produce the reference's padded layout
+    (model_clip.py:531-552, dataset_voa.py:532-544,566-577); a packing-aware encoder would emit the rows
+    directly.  One host read (the maximum count) -- do it in the data loader, not in the step."""
+    if drop_first:
+        vec, num = vec[:, 1:], num[:, 1:]
+    valid = num != 0
+    counts = valid.sum(dim=1)
+    offsets = torch.zeros(vec.shape[0] + 1, dtype=torch.int32, device=vec.device)
+    offsets[1:] = counts.cumsum(0)
+    rows = vec[valid]            # boolean-mask gather keeps sample order and node order; autograd-connected
+    return PackedNodes(rows.contiguous(), offsets, int(counts.max().item()) if vec.shape[0] else 0)
+
+
+class _OtAlignmentPacked(torch.autograd.Function):
+    """(text rows, image rows) in packed layout -> (loss, dist[B]); gradients come back packed."""
+
+    @staticmethod
+    def forward(ctx, txt_rows, img_rows, txt_off, img_off, max_m, max_n, beta, iters, k, loss_scale):
+        L.require_cuda(txt_rows, img_rows, txt_off, img_off)
+        if txt_rows.dtype != img_rows.dtype or txt_rows.dim() != 2 or img_rows.dim() != 2 or txt_rows.shape[1] != img_rows.shape[1]:
+            raise RuntimeError("expected [sum_m, D] text rows and [sum_n, D] image rows of one dtype")
+        if txt_off.dtype != torch.int32 or img_off.dtype != torch.int32 or txt_off.numel() != img_off.numel():
+            raise RuntimeError("offsets must be int32 [B+1] vectors")
+        B, D = txt_off.numel() - 1, txt_rows.shape[1]
+        dev = txt_rows.device
+        tr, ir = txt_rows.detach().contiguous(), img_rows.detach().contiguous()
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        dist = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        if need_grad:
+            n_t = tr.numel()
+            n_t_pad = (n_t + 7) // 8 * 8
+            gbuf = torch.empty(n_t_pad + ir.numel(), dtype=tr.dtype, device=dev)
+            if n_t_pad != n_t:
+                gbuf[n_t:n_t_pad].zero_()
+            dtxt, dimg = gbuf[:n_t].view_as(tr), gbuf[n_t_pad:].view_as(ir)
+        else:
+            gbuf = dtxt = dimg = None
+        L.check(L.load().ce_ot_fwd_bwd_packed(
+            tr.data_ptr(), txt_off.data_ptr(), ir.data_ptr(), img_off.data_ptr(), B, int(max_m), int(max_n), D,
+            L.dtype_code(tr.dtype), float(beta), int(iters), int(k), float(loss_scale), dist.data_ptr(), loss.data_ptr(),
+            L.ptr(dtxt), L.ptr(dimg), L.stream_ptr()), "packed OT forward")
+        ctx.stash = (dtxt, dimg, gbuf)
+        ctx.loss_scale = float(loss_scale)
+        ctx.set_materialize_grads(False)
+        return loss[0], dist
+
+    @staticmethod
+    def backward(ctx, g_loss, g_dist):
+        dtxt, dimg, gbuf = ctx.stash
+        if dtxt is None:
+            return (None,) * 10
+        if g_dist is not None:
+            raise RuntimeError("packed OT: per-sample upstream gradients are not supported; use the padded optimal_transport_dist")
+        ctx.stash = (None, None, None)
+        g = _scalar_f32(g_loss, dtxt.device)
+        L.check(L.load().ce_scale_inplace(gbuf.data_ptr(), 1, gbuf.numel(), gbuf.numel(), L.dtype_code(dtxt.dtype),
+                                          g.data_ptr(), L.stream_ptr()), "packed OT backward scale")
+        return dtxt, dimg, None, None, None, None, None, None, None, None
+
+
+def ot_alignment_packed(txt: PackedNodes, img: PackedNodes, beta=IPOT_BETA, iters=IPOT_ITERS, k=IPOT_K,
+                        loss_scale=OT_LOSS_WEIGHT):
+    """(loss_scale * sum_b dist[b], dist[B]) for packed node sets (bf16, at most 16 text and 64 image nodes per
+    sample, D a multiple of 64 up to 512 -- the streaming kernel; anything else is padded on the device and
+    goes through :func:`ot_alignment`).  Equal to the padded, masked call."""
+    D = txt.rows.shape[1]
+    ok = (txt.rows.dtype == torch.bfloat16 and 1 <= txt.max_count <= 16 and 1 <= img.max_count <= 64
+          and D % 64 == 0 and D <= 512)
+    if ok:
+        return _OtAlignmentPacked.apply(txt.rows, img.rows, txt.offsets, img.offsets, txt.max_count, img.max_count,
+                                        beta, iters, k, loss_scale)
+    tp, tm = txt.to_padded(max(txt.max_count, 1))
+    ip, im = img.to_padded(max(img.max_count, 1))
+    return ot_alignment(tp, ip, tm, im, drop_slot0=False, beta=beta, iters=iters, k=k, loss_scale=loss_scale)
+
+
+# --------------------------------------------------------------------------------------------
 # one call for engine.py:48-67,88: both criteria, two streams, gradients formed with the losses
 # --------------------------------------------------------------------------------------------
 _SIDE_STREAMS = {}

@@ -179,6 +179,18 @@ int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* img, int64_t
                   void* dtxt, void* dimg, void* dimg_slot0, void* workspace,
                   size_t workspace_bytes, ce_stream_t stream);
 
+/* Packed (variable-length) node sets -- SURVEY.md 8f-3; the reference pads every sample to the batch maximum
+ * (model_clip.py:531-552, dataset_voa.py:532-544,566-577) and masks the padding afterwards.  Here the rows of
+ * sample b are txt_off[b] .. txt_off[b+1]-1 of a dense [sum_m, D] matrix (img_off likewise, the whole-image slot
+ * already removed); every row is a valid node.  bf16, max_m <= 16, max_n <= 64, D a multiple of 64 up to 512
+ * (CE_ERR_SHAPE otherwise: pad and call ce_ot_fwd_bwd).  dtxt_rows / dimg_rows (both or neither) receive
+ * loss_scale * d(sum dist)/d(rows) in the same packed layout.  Same value as ce_ot_fwd_bwd on the padded,
+ * masked batch. */
+int ce_ot_fwd_bwd_packed(const void* txt_rows, const int32_t* txt_off, const void* img_rows,
+                         const int32_t* img_off, int B, int max_m, int max_n, int D, int dtype,
+                         float beta, int iters, int k, float loss_scale, float* dist, float* loss,
+                         void* dtxt_rows, void* dimg_rows, ce_stream_t stream);
+
 /* The solver's building blocks with the reference's own granularity (model_ot.py), fp32:
  *   ce_ot_cost_matrix : cost_matrix_cosine  [B,M,D],[B,N,D] -> 1 - cos [B,M,N]  (model_ot.py:8-18)
  *   ce_ot_ipot        : ipot                C [B,M,N] -> T [B,N,M]              (model_ot.py:32-63)

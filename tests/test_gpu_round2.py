@@ -270,6 +270,50 @@ def test_contrastive_parity_with_stored_exponentials_forced():
 
 
 # ------------------------------------------------------------------------------------------
+# packed (variable-length) node sets -- same numbers as the padded, masked batch
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,M,N,D,masks", [(64, 16, 50, 512, "ragged"), (37, 9, 64, 256, "ragged"), (130, 16, 50, 512, "edge"),
+                                           (33, 5, 17, 128, "scattered"), (300, 16, 50, 512, "full")])
+def test_packed_alignment_equals_padded(B, M, N, D, masks):
+    etxt, obj, tnum, onum = syn.ot_inputs(B, M, N, D, 21, masks, dtype=torch.bfloat16)
+    etxt, obj, tnum, onum = etxt.cuda(), obj.cuda(), tnum.cuda(), onum.cuda()
+    a_t, a_o = etxt.clone().requires_grad_(True), obj.clone().requires_grad_(True)
+    ref = ce.CriterionAlignment()(a_t, a_o, tnum, onum)["loss_ot"]
+    ref.float().backward()
+    b_t, b_o = etxt.clone().requires_grad_(True), obj.clone().requires_grad_(True)
+    head = ce.ClipEventHead()
+    img_nodes, txt_nodes = head.sim_entity_packed(b_o, b_t, onum, tnum)
+    assert txt_nodes.rows.shape[0] == int((tnum != 0).sum()) and img_nodes.rows.shape[0] == int((onum[:, 1:] != 0).sum())
+    got = ce.CriterionAlignment().forward_packed(txt_nodes, img_nodes)["loss_ot"]
+    got.float().backward()
+    torch.cuda.synchronize()
+    assert got.item() == ref.item()
+    # gradients: valid nodes agree with the padded path (same kernel, same arithmetic), padding gets zero
+    tv, ov = (tnum != 0), (onum != 0)
+    ov[:, 0] = False
+    assert rel_err(b_t.grad[tv], a_t.grad[tv]) < 1e-5 and rel_err(b_o.grad[ov], a_o.grad[ov]) < 1e-5
+    assert float(b_t.grad[~tv].abs().max() if (~tv).any() else 0.0) == 0.0
+    assert float(b_o.grad[~ov].abs().max()) == 0.0
+    # and against the fp64 oracle
+    d_ref, dx_ref, dy_ref = orc.ot_closed_form_grads(etxt.double().cpu(), obj.double().cpu()[:, 1:], (tnum == 0).cpu(),
+                                                     (onum[:, 1:] == 0).cpu(), torch.full((B,), 0.01, dtype=torch.float64))
+    with torch.no_grad():   # the criterion rounds its loss to the input dtype (bf16, as the reference does): take the fp32 value
+        loss32, dist32 = F_.ot_alignment_packed(txt_nodes, img_nodes)
+    assert abs(loss32.item() - 0.01 * d_ref.sum().item()) <= 2e-3 * abs(0.01 * d_ref.sum().item()) + 1e-6
+    assert rel_err(dist32, d_ref) < 2e-3
+    assert rel_err(b_t.grad, dx_ref) < 1e-2 and rel_err(b_o.grad[:, 1:], dy_ref) < 1e-2
+
+
+def test_packed_alignment_falls_back_to_padding_for_other_shapes():
+    etxt, obj, tnum, onum = syn.ot_inputs(12, 20, 70, 128, 5, "ragged", dtype=torch.float32)
+    etxt, obj, tnum, onum = etxt.cuda(), obj.cuda(), tnum.cuda(), onum.cuda()
+    ref = ce.CriterionAlignment()(etxt, obj, tnum, onum)["loss_ot"]
+    img_nodes, txt_nodes = ce.ClipEventHead().sim_entity_packed(obj, etxt, onum, tnum)
+    got = ce.CriterionAlignment().forward_packed(txt_nodes, img_nodes)["loss_ot"]
+    assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-7
+
+
+# ------------------------------------------------------------------------------------------
 # engine.py:89-90 on the head's own parameter: clip_grad_norm_ + optimizer.step() in one launch
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["sgd", "adam"])

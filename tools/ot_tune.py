@@ -34,3 +34,18 @@ def time_it(fn, n=20):
 l, d = fwd()
 print("%s %s B=%d: fwd(cost+ipot) %.1f us   full %.1f us   loss %.6f" % (
     wl, sys.argv[2], B, time_it(fwd), time_it(full), l.item()))
+# packed (variable-length) layout of the same batch: SURVEY 8f-3
+if dt == torch.bfloat16 and w.M <= 16 and w.N <= 64 and w.D <= 512:
+    tp = F_.pack_nodes(etxt, tnum)
+    ip = F_.pack_nodes(obj, onum, drop_first=True)
+    trg, irg = tp.rows.clone().requires_grad_(True), ip.rows.clone().requires_grad_(True)
+    tpg, ipg = F_.PackedNodes(trg, tp.offsets, tp.max_count), F_.PackedNodes(irg, ip.offsets, ip.max_count)
+    def full_packed():
+        trg.grad = None; irg.grad = None
+        l, _ = F_.ot_alignment_packed(tpg, ipg)
+        l.backward()
+    lp, _ = F_.ot_alignment_packed(tp, ip)
+    nbytes = 2 * 2 * (tp.rows.numel() + ip.rows.numel())
+    tpk = time_it(full_packed)
+    print("%s packed: full %.1f us  (%d of %d node rows are valid: %.0f MB in + out -> %.0f GB/s)  loss %.6f" % (
+        wl, tpk, tp.rows.shape[0] + ip.rows.shape[0], B * (w.M + w.N), nbytes / 1e6, nbytes / tpk / 1e3, lp.item()))
