@@ -176,6 +176,9 @@ __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.al
 template <int REGS>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
+// PACKED: variable-length node sets (offset arrays instead of masks); a separate instantiation so that the padded
+// kernel does not carry its code (the kernel is sensitive to its instruction footprint)
+template <bool PACKED>
 __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int RS = a.D * 2 + 16;                       // row stride of a chunk buffer in bytes
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
   const int g = lane >> 2, t = lane & 3;
   const int count = (a.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool grads = a.dtxt != nullptr;
-  const bool packed = a.txt_off != nullptr;
+  constexpr bool packed = PACKED;
   // per-sample geometry: element offsets of the sample's first text / image row and its node counts
   auto sample_geom = [&](int64_t b, int64_t& xo, int64_t& yo, int& m, int& n) {
     if (packed) {
@@ -249,10 +252,13 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
     const int R = cost_side ? CY : GY;
     int q = 0;                                       // y chunk sequence number: ring slot q % R, use q / R
     int qs = 0, qu = 0;                              // q % R and (q / R) & 1 without the divisions
+    // the geometry of sample k+1 is fetched while sample k is being loaded (packed layout: two offsets per side;
+    // their global-load latency would otherwise sit in this serial chain once per sample)
+    int64_t xo_n = 0, yo_n = 0; int m_n = 0, n_n = 0;
+    sample_geom((int64_t)blockIdx.x, xo_n, yo_n, m_n, n_n);
     for (int k = 0; k < count; ++k) {
-      const int64_t b = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-      int64_t xo, yo; int m_b, n_b;
-      sample_geom(b, xo, yo, m_b, n_b);
+      const int64_t xo = xo_n, yo = yo_n; const int m_b = m_n, n_b = n_n;
+      if (k + 1 < count) sample_geom((int64_t)blockIdx.x + (int64_t)(k + 1) * gridDim.x, xo_n, yo_n, m_n, n_n);
       const uint8_t* xg = reinterpret_cast<const uint8_t*>(a.txt) + xo * 2;
       const uint8_t* yg = reinterpret_cast<const uint8_t*>(a.img) + yo * 2;
       const int xs = k & 1;
@@ -275,10 +281,11 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
     // ===================================== storer ================================================
     if (!grads) return;
     int qs = 0, qu = 0;
+    int64_t xo_n = 0, yo_n = 0; int m_n = 0, n_n = 0;
+    sample_geom((int64_t)blockIdx.x, xo_n, yo_n, m_n, n_n);
     for (int k = 0; k < count; ++k) {
-      const int64_t b = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-      int64_t xo, yo; int m_b, n_b;
-      sample_geom(b, xo, yo, m_b, n_b);
+      const int64_t xo = xo_n, yo = yo_n; const int m_b = m_n, n_b = n_n;
+      if (k + 1 < count) sample_geom((int64_t)blockIdx.x + (int64_t)(k + 1) * gridDim.x, xo_n, yo_n, m_n, n_n);
       uint8_t* dxg = reinterpret_cast<uint8_t*>(a.dtxt) + xo * 2;
       uint8_t* dyg = reinterpret_cast<uint8_t*>(a.dimg) + yo * 2;
       for (int c = 0; c < NC; ++c) {
@@ -675,17 +682,18 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
       const int park = k % P;
       const int xs = k & 1;
       ParkScratch& sc = scr[park];
+      int n_b = a.N;
+      if (packed) {   // issued before the wait: its latency hides behind the solve
+        const int64_t b = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+        n_b = __ldg(a.img_off + b + 1) - __ldg(a.img_off + b);
+      }
       role_wait(&bars->w_ready[park], (k / P) & 1, lane, sleep_ns);
       if (gw == 0) OT_TRACE(k, 6);
       if (!grads) {
         role_arrive(&bars->scr_free[park], lane);
         continue;
       }
-      int n_b = a.N;
-      if (packed) {
-        const int64_t b = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-        n_b = __ldg(a.img_off + b + 1) - __ldg(a.img_off + b);
-      }
+
       // W, ax, ay move to the hand-over buffer so that the scratch goes back to the cost warps at once.  (Keeping
       // the fragments of all four chunks in registers instead needs the chunk loop unrolled: four times the code,
       // measured 8 % slower -- the kernel is sensitive to its instruction footprint.)
@@ -826,8 +834,13 @@ int launch_ot_stream(OtFusedArgs a, cudaStream_t st) {
     static const int sl = [] { const char* e = getenv("CE_OT_SLEEP"); return e ? atoi(e) : 0; }();
     a.poll_mode = sl;
   }
-  CE_CUDA_TRY(cudaFuncSetAttribute(ot_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ot_stream_kernel<<<grid, kThreads, smem, st>>>(a);
+  if (a.txt_off != nullptr) {
+    CE_CUDA_TRY(cudaFuncSetAttribute(ot_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ot_stream_kernel<true><<<grid, kThreads, smem, st>>>(a);
+  } else {
+    CE_CUDA_TRY(cudaFuncSetAttribute(ot_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ot_stream_kernel<false><<<grid, kThreads, smem, st>>>(a);
+  }
   CE_LAUNCH_CHECK();
   return CE_OK;
 }
