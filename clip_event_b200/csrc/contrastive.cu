@@ -406,6 +406,13 @@ struct EpiStore {
         }
         *reinterpret_cast<float4*>(o + i) = v;
       }
+    } else if (p.atomic == 1 && (p.ldo % 4 == 0) && (col0 + 32 <= p.N)) {
+      // split-K / accumulate: 16-byte vector reductions (red.global.add.v4.f32), a quarter of the L2 operations
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        atomicAdd(reinterpret_cast<float4*>(o + i),
+                  make_float4(acc[i] * rs * s_epi[lcol0 + i], acc[i + 1] * rs * s_epi[lcol0 + i + 1],
+                              acc[i + 2] * rs * s_epi[lcol0 + i + 2], acc[i + 3] * rs * s_epi[lcol0 + i + 3]));
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -1019,8 +1026,11 @@ __global__ void bwd_onehot_kernel(BwdFixArgs a, int side) {
     float u[8], v[8];
     In<CE_BF16>::load16(xa + c0, u);
     In<CE_BF16>::load16(xb + c0, v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { atomicAdd(da + c0 + i, ca * u[i]); atomicAdd(db + c0 + i, cb * v[i]); }
+    // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the L2 atomic operations of scalar adds
+    atomicAdd(reinterpret_cast<float4*>(da + c0), make_float4(ca * u[0], ca * u[1], ca * u[2], ca * u[3]));
+    atomicAdd(reinterpret_cast<float4*>(da + c0 + 4), make_float4(ca * u[4], ca * u[5], ca * u[6], ca * u[7]));
+    atomicAdd(reinterpret_cast<float4*>(db + c0), make_float4(cb * v[0], cb * v[1], cb * v[2], cb * v[3]));
+    atomicAdd(reinterpret_cast<float4*>(db + c0 + 4), make_float4(cb * v[4], cb * v[5], cb * v[6], cb * v[7]));
   }
 }
 

@@ -13,9 +13,12 @@ timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-secondar
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${R}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-secondary > gpurun_out/${R}_ncu_launches.log 2>&1
 timeout 120 python tools/ot_tune.py c3 bf16 > gpurun_out/${R}_ot_tune_c3.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:ot_fused" -s 6 -c 2 \
-    -o gpurun_out/prof_${R}_ot_fused python tools/ot_tune.py c3 bf16 > gpurun_out/${R}_ncu_ot.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:ot_stream" -s 32 -c 1 \
+    -o gpurun_out/prof_${R}_ot_stream python tools/ot_tune.py c3 bf16 > gpurun_out/${R}_ncu_ot.log 2>&1
 timeout 120 python tools/con_tune.py c3 bf16 > gpurun_out/${R}_con_tune_c3.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:fwd_items|normalize_bwd|prep_all" -s 12 -c 4 \
-    -o gpurun_out/prof_${R}_smallkernels python tools/con_tune.py c3 bf16 > gpurun_out/${R}_ncu_small.log 2>&1
-tail -n 2 gpurun_out/${R}_con_tune_c3.log; tail -n 2 gpurun_out/${R}_ot_tune_c3.log
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:umma_gemm" -s 24 -c 8 \
+    -o gpurun_out/prof_${R}_gemm_chain python tools/con_tune.py c3 bf16 > gpurun_out/${R}_ncu_gemm.log 2>&1
+timeout 120 python tools/ot_tune.py c4 bf16 > gpurun_out/${R}_ot_tune_c4.log 2>&1
+timeout 300 python bench.py --workload c4 --steps 20 --warmup 5 --no-cpu-baseline --no-secondary > gpurun_out/${R}_bench_c4.json 2> gpurun_out/${R}_bench_c4.err
+timeout 300 python bench.py --workload c2 --steps 20 --warmup 5 --no-cpu-baseline --no-secondary > gpurun_out/${R}_bench_c2.json 2> gpurun_out/${R}_bench_c2.err
+tail -n 2 gpurun_out/${R}_con_tune_c3.log; tail -n 3 gpurun_out/${R}_ot_tune_c3.log; tail -n 2 gpurun_out/${R}_ot_tune_c4.log
