@@ -1061,16 +1061,16 @@ __global__ void __launch_bounds__(256) bwd_dls_dot_kernel(const void* img, const
   }
 }
 
-// Host-side gate (the same decision in forward and backward).  Measured (bf16, one B200): 4096 x 36864 logits
-// 607 -> 559 us per forward + backward; 1024 x 9216 176 -> 186 us and 256 x 2304 92 -> 104 us (the saved recompute
-// GEMM no longer outweighs the extra launches and the store; per-rank shards of c3: 4096 x 18432 354 -> 342 us,
-// 4096 x 9216 216 -> 216 us, 4096 x 4608 153 -> 156 us), so problems below 2^26 logits keep the recompute path.
+// Host-side gate (the same decision in forward and backward).  Measured (bf16, one B200, forward + backward):
+// 4096 x 36864 logits 560 -> 504 us; per-rank shards of c3: 4096 x 18432 342 -> 288 us, 4096 x 9216 201 -> 189 us,
+// 4096 x 4608 136 -> 131 us; 1024 x 9216 (c4) 147 -> 148 us and 256 x 2304 (c2) slower (the saved recompute GEMM
+// no longer outweighs the extra launches and the store), so problems below 2^24 logits keep the recompute path.
 // CE_CTR_STORED=0 / 2 (tuning aid) forces the path off / on.
 inline bool stored_exp_enabled(int R, int C) {
   static const int mode = [] { const char* e = getenv("CE_CTR_STORED"); return e == nullptr ? 1 : atoi(e); }();
   if (mode == 0) return false;
   if (mode == 2) return true;
-  return (int64_t)R * C >= (int64_t)1 << 26;
+  return (int64_t)R * C >= (int64_t)1 << 24;
 }
 
 // ------------------------------------------------------------------------------------------
