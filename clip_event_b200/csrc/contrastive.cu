@@ -1534,6 +1534,229 @@ extern "C" int ce_contrastive_bwd(const void* img, const void* txt, const float*
   return ce_contrastive_bwd_finish(img, w.dimg_hat, B, D, dtype, dimg, stream);
 }
 
+// ------------------------------------------------------------------------------------------
+// the projections that feed the head.  Image side (model_clip.py:253-260):
+// x[:, 0, :] -> ln_post -> @ proj; text side (model_clip.py:412-415): ln_final -> x[arange, eot] ->
+// @ text_projection (LayerNorm is per token, so selecting the token first is the same).  One row
+// kernel gathers the token row straight out of the [rows, L, W] hidden states, normalises it in fp32
+// and writes the GEMM operand (bf16, or tf32 hi/lo); the projection runs on the tcgen05 GEMM; the
+// finishing kernel writes the features in the input dtype together with their squared L2 norms
+// (what the head's preparation needs next).  Backward: two GEMMs + the LayerNorm backward rows.
+// ------------------------------------------------------------------------------------------
+namespace ce {
+namespace {
+
+struct ProjWs {
+  float *mu, *rstd;          // [rows]
+  void* y[2];                // LayerNorm output: bf16 [rows, W], or tf32 hi / lo fp32
+  void* pj[2];               // fp32 mode: tf32 hi / lo of proj [W, D]
+  void* df[2];               // fp32 mode: tf32 hi / lo of dfeat [rows, D]
+  float* acc;                // fp32 [rows, max(W, D)]: GEMM outputs
+  size_t bytes;
+};
+ProjWs proj_carve(void* base, int rows, int W, int D, int dtype) {
+  ProjWs w{};
+  Carver cv(base);
+  w.mu = cv.take<float>(rows); w.rstd = cv.take<float>(rows);
+  if (dtype == CE_F32) {
+    for (int i = 0; i < 2; ++i) {
+      w.y[i] = cv.take<float>((size_t)rows * W);
+      w.pj[i] = cv.take<float>((size_t)W * D);
+      w.df[i] = cv.take<float>((size_t)rows * D);
+    }
+  } else {
+    w.y[0] = cv.take<__nv_bfloat16>((size_t)rows * W);
+  }
+  w.acc = cv.take<float>((size_t)rows * (W > D ? W : D));
+  w.bytes = cv.used() + 1024;
+  return w;
+}
+
+// one warp per row: gather, LayerNorm (fp32 statistics, two passes over the row in registers/L1), GEMM operand
+template <int DT>
+__global__ void proj_ln_kernel(const void* hidden, int64_t sample_stride, const int64_t* token, const void* ln_w,
+                               const void* ln_b, float eps, int rows, int W, float* mu_out, float* rstd_out,
+                               void* y0, void* y1) {
+  using T = typename In<DT>::type;
+  constexpr int V = In<DT>::kVec;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const T* x = reinterpret_cast<const T*>(hidden) + (int64_t)r * sample_stride + (token != nullptr ? token[r] : 0) * (int64_t)W;
+  float s = 0.f;
+  for (int c = lane * V; c < W; c += 32 * V) {
+    float v[8];
+    In<DT>::load16(x + c, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += v[i];
+  }
+  const float mu = warp_sum(s) / (float)W;
+  float q = 0.f;
+  for (int c = lane * V; c < W; c += 32 * V) {
+    float v[8];
+    In<DT>::load16(x + c, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) q += (v[i] - mu) * (v[i] - mu);
+  }
+  const bool ln = ln_w != nullptr;
+  const float rstd = ln ? rsqrtf(warp_sum(q) / (float)W + eps) : 1.f;
+  const float m = ln ? mu : 0.f;
+  if (lane == 0) { mu_out[r] = m; rstd_out[r] = rstd; }
+  const T* gw = reinterpret_cast<const T*>(ln_w);
+  const T* gb = reinterpret_cast<const T*>(ln_b);
+  for (int c = lane * V; c < W; c += 32 * V) {
+    float v[8], wv[8], bv[8];
+    In<DT>::load16(x + c, v);
+    if (ln) { In<DT>::load16(gw + c, wv); In<DT>::load16(gb + c, bv); }
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < V; ++i) y[i] = ln ? (v[i] - m) * rstd * wv[i] + bv[i] : v[i];
+    if constexpr (DT == CE_F32) {
+      float hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { hi[i] = __uint_as_float(f2tf32(y[i])); lo[i] = __uint_as_float(f2tf32(y[i] - hi[i])); }
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(y0) + (int64_t)r * W + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(y1) + (int64_t)r * W + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    } else {
+      uint4 pk;
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(y[0], y[1]), t1 = __floats2bfloat162_rn(y[2], y[3]);
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(y[4], y[5]), t3 = __floats2bfloat162_rn(y[6], y[7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+      pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y0) + (int64_t)r * W + c) = pk;
+    }
+  }
+}
+
+// fp32 [rows, D] -> features in the I/O dtype + squared L2 norm of the STORED (rounded) row
+template <int DT>
+__global__ void proj_finish_kernel(const float* acc, int rows, int D, void* feat, float* norm2) {
+  using T = typename In<DT>::type;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = acc[(int64_t)r * D + c];
+    In<DT>::st(reinterpret_cast<T*>(feat) + (int64_t)r * D + c, v);
+    const float vr = DT == CE_F32 ? v : __bfloat162float(__float2bfloat16_rn(v));   // the value as stored
+    ss += vr * vr;
+  }
+  ss = warp_sum(ss);
+  if (lane == 0 && norm2 != nullptr) norm2[r] = ss;
+}
+
+// LayerNorm backward of the gathered rows; dln_w / dln_b are accumulated with red.add (zeroed by the caller)
+template <int DT>
+__global__ void proj_ln_bwd_kernel(const void* hidden, int64_t sample_stride, const int64_t* token, const void* ln_w,
+                                   const float* mu, const float* rstd, const float* dy, int rows, int W, void* dx,
+                                   float* dln_w, float* dln_b) {
+  using T = typename In<DT>::type;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const T* x = reinterpret_cast<const T*>(hidden) + (int64_t)r * sample_stride + (token != nullptr ? token[r] : 0) * (int64_t)W;
+  const float* g = dy + (int64_t)r * W;
+  T* o = reinterpret_cast<T*>(dx) + (int64_t)r * W;
+  if (ln_w == nullptr) {
+    for (int c = lane; c < W; c += 32) In<DT>::st(o + c, g[c]);
+    return;
+  }
+  const T* gw = reinterpret_cast<const T*>(ln_w);
+  const float m = mu[r], rs = rstd[r];
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < W; c += 32) {
+    const float xh = (In<DT>::ld(x + c) - m) * rs, dh = g[c] * In<DT>::ld(gw + c);
+    s1 += dh; s2 += dh * xh;
+    atomicAdd(dln_w + c, g[c] * xh);
+    atomicAdd(dln_b + c, g[c]);
+  }
+  s1 = warp_sum(s1) / (float)W; s2 = warp_sum(s2) / (float)W;
+  for (int c = lane; c < W; c += 32) {
+    const float xh = (In<DT>::ld(x + c) - m) * rs, dh = g[c] * In<DT>::ld(gw + c);
+    In<DT>::st(o + c, rs * (dh - s1 - xh * s2));
+  }
+}
+
+template <int DT>
+int proj_fwd_impl(const void* hidden, int64_t sample_stride, const int64_t* token, const void* ln_w, const void* ln_b,
+                  float eps, const void* proj, int rows, int W, int D, void* feat, float* norm2, ProjWs& w, cudaStream_t st) {
+  constexpr bool TF = DT == CE_F32;
+  const int blocks = (rows * 32 + 255) / 256;
+  proj_ln_kernel<DT><<<blocks, 256, 0, st>>>(hidden, sample_stride, token, ln_w, ln_b, eps, rows, W, w.mu, w.rstd, w.y[0], w.y[1]);
+  CE_LAUNCH_CHECK();
+  if (TF) CE_TRY((run_prep<CE_F32>(proj, nullptr, W, D, nullptr, nullptr, w.pj[0], w.pj[1], st)));
+  // feat = y [rows, W] (K-major) x proj [K = W, N = D] (row-major = MN-major B)
+  CE_TRY((plain_gemm<TF>(operand<DT>(w.y[0], w.y, rows, W, 0), operand<DT>(proj, w.pj, D, D, 1), W, w.acc, D, nullptr, nullptr, false, st)));
+  proj_finish_kernel<DT><<<blocks, 256, 0, st>>>(w.acc, rows, D, feat, norm2);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}
+
+template <int DT>
+int proj_bwd_impl(const void* hidden, int64_t sample_stride, const int64_t* token, const void* ln_w, const void* proj,
+                  const void* dfeat, int rows, int W, int D, void* dx_rows, float* dln_w, float* dln_b, float* dproj,
+                  ProjWs& w, cudaStream_t st) {
+  constexpr bool TF = DT == CE_F32;
+  if (TF) {
+    CE_TRY((run_prep<CE_F32>(proj, nullptr, W, D, nullptr, nullptr, w.pj[0], w.pj[1], st)));
+    CE_TRY((run_prep<CE_F32>(dfeat, nullptr, rows, D, nullptr, nullptr, w.df[0], w.df[1], st)));
+  }
+  // dproj [W, D] = y^t [M = W, K = rows] (y is [rows, W]: MN-major A) x dfeat [K = rows, N = D] (MN-major B)
+  CE_TRY((plain_gemm<TF>(operand<DT>(w.y[0], w.y, W, W, 1), operand<DT>(dfeat, w.df, D, D, 1), rows, dproj, D, nullptr, nullptr, false, st)));
+  // dy [rows, W] = dfeat [rows, K = D] x proj^t: proj is [N = W, K = D] row-major, a K-major B operand
+  CE_TRY((plain_gemm<TF>(operand<DT>(dfeat, w.df, rows, D, 0), operand<DT>(proj, w.pj, W, D, 0), D, w.acc, W, nullptr, nullptr, false, st)));
+  if (ln_w != nullptr) {
+    CE_CUDA_TRY(cudaMemsetAsync(dln_w, 0, sizeof(float) * W, st));
+    CE_CUDA_TRY(cudaMemsetAsync(dln_b, 0, sizeof(float) * W, st));
+  }
+  proj_ln_bwd_kernel<DT><<<(rows * 32 + 255) / 256, 256, 0, st>>>(hidden, sample_stride, token, ln_w, w.mu, w.rstd, w.acc, rows, W,
+                                                                 dx_rows, dln_w, dln_b);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}
+
+int proj_check(int rows, int W, int D, int dtype, const void* a, const void* b) {
+  if (dtype != CE_F32 && dtype != CE_BF16) return fail(CE_ERR_DTYPE, "projection: unknown dtype %d", dtype);
+  if (rows < 1 || W < 8 || D < 8 || W % 8 || D % 8) return fail(CE_ERR_SHAPE, "projection: need rows >= 1 and W, D positive multiples of 8 (rows=%d W=%d D=%d)", rows, W, D);
+  if (((uintptr_t)a | (uintptr_t)b) & 15) return fail(CE_ERR_ALIGN, "projection: hidden states and proj must be 16-byte aligned");
+  return CE_OK;
+}
+
+}  // namespace
+}  // namespace ce
+
+extern "C" size_t ce_proj_workspace_bytes(int rows, int W, int D, int dtype) {
+  if (rows < 1 || W < 1 || D < 1) return 0;
+  return proj_carve(nullptr, rows, W, D, dtype).bytes;
+}
+
+extern "C" int ce_proj_fwd(const void* hidden, int64_t sample_stride, const int64_t* token_index, const void* ln_w,
+                           const void* ln_b, float eps, const void* proj, int rows, int W, int D, int dtype,
+                           void* feat, float* norm2, void* workspace, size_t workspace_bytes, ce_stream_t stream) {
+  CE_TRY(check_device());
+  CE_TRY(proj_check(rows, W, D, dtype, hidden, proj));
+  if ((ln_w == nullptr) != (ln_b == nullptr)) return fail(CE_ERR_ARG, "projection: pass both LayerNorm vectors or neither");
+  const int64_t esz = dtype == CE_F32 ? 4 : 2;
+  if ((sample_stride * esz) % 16) return fail(CE_ERR_ALIGN, "projection: the sample stride must keep 16-byte alignment");
+  ProjWs w = proj_carve(workspace, rows, W, D, dtype);
+  if (workspace_bytes < w.bytes) return fail(CE_ERR_WORKSPACE, "projection: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == CE_F32) return proj_fwd_impl<CE_F32>(hidden, sample_stride, token_index, ln_w, ln_b, eps, proj, rows, W, D, feat, norm2, w, st);
+  return proj_fwd_impl<CE_BF16>(hidden, sample_stride, token_index, ln_w, ln_b, eps, proj, rows, W, D, feat, norm2, w, st);
+}
+
+extern "C" int ce_proj_bwd(const void* hidden, int64_t sample_stride, const int64_t* token_index, const void* ln_w,
+                           const void* proj, const void* dfeat, int rows, int W, int D, int dtype, void* dx_rows,
+                           float* dln_w, float* dln_b, float* dproj, void* workspace, size_t workspace_bytes,
+                           ce_stream_t stream) {
+  CE_TRY(check_device());
+  CE_TRY(proj_check(rows, W, D, dtype, hidden, proj));
+  if (((uintptr_t)dfeat | (uintptr_t)dx_rows | (uintptr_t)dproj) & 15) return fail(CE_ERR_ALIGN, "projection: gradient buffers must be 16-byte aligned");
+  ProjWs w = proj_carve(workspace, rows, W, D, dtype);
+  if (workspace_bytes < w.bytes) return fail(CE_ERR_WORKSPACE, "projection: workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == CE_F32) return proj_bwd_impl<CE_F32>(hidden, sample_stride, token_index, ln_w, proj, dfeat, rows, W, D, dx_rows, dln_w, dln_b, dproj, w, st);
+  return proj_bwd_impl<CE_BF16>(hidden, sample_stride, token_index, ln_w, proj, dfeat, rows, W, D, dx_rows, dln_w, dln_b, dproj, w, st);
+}
+
 extern "C" size_t ce_similarity_workspace_bytes(int Ra, int Rb, int D, int dtype) {
   size_t b = 4 * 256 + sizeof(float) * ((size_t)Ra + Rb);
   if (dtype == CE_F32) b += 2 * sizeof(float) * ((size_t)Ra + Rb) * D + 4 * 256;

@@ -319,6 +319,72 @@ def ot_alignment(txt_nodes, object_vec, txt_mask, object_mask, drop_slot0=True, 
 
 
 # --------------------------------------------------------------------------------------------
+# the projections that feed the head (model_clip.py:253-260 and :412-415)
+# --------------------------------------------------------------------------------------------
+class _ProjectionTail(torch.autograd.Function):
+    """hidden [rows, L, W] -> LayerNorm(hidden[arange, token]) @ proj  ([rows, D]); gradients for the hidden
+    states (non-zero at the selected token only), the LayerNorm vectors and the projection."""
+
+    @staticmethod
+    def forward(ctx, hidden, token_index, ln_w, ln_b, proj, eps):
+        L.require_cuda(hidden, proj)
+        if hidden.dim() != 3 or proj.dim() != 2 or hidden.shape[2] != proj.shape[0]:
+            raise RuntimeError("expected hidden [rows, L, W] and proj [W, D]")
+        if proj.dtype != hidden.dtype or (ln_w is not None and (ln_w.dtype != hidden.dtype or ln_b.dtype != hidden.dtype)):
+            raise RuntimeError("hidden states, LayerNorm vectors and the projection must share a dtype")
+        dt = L.dtype_code(hidden.dtype)
+        h = hidden.detach().contiguous()
+        pj = proj.detach().contiguous()
+        rows, Lt, W = h.shape
+        D = pj.shape[1]
+        dev = h.device
+        tok = None if token_index is None else token_index.to(device=dev, dtype=torch.int64).contiguous()
+        lw = None if ln_w is None else ln_w.detach().contiguous()
+        lb = None if ln_b is None else ln_b.detach().contiguous()
+        lib = L.load()
+        nbytes = lib.ce_proj_workspace_bytes(rows, W, D, dt)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        feat = torch.empty(rows, D, dtype=h.dtype, device=dev)
+        norm2 = torch.empty(rows, dtype=torch.float32, device=dev)
+        L.check(lib.ce_proj_fwd(h.data_ptr(), Lt * W, L.ptr(tok), L.ptr(lw), L.ptr(lb), float(eps), pj.data_ptr(), rows, W, D, dt,
+                                feat.data_ptr(), norm2.data_ptr(), ws.data_ptr(), nbytes, L.stream_ptr()), "projection forward")
+        ctx.save_for_backward(h, tok, lw, pj, ws)
+        ctx.has_ln = lw is not None
+        ctx.mark_non_differentiable(norm2)
+        return feat, norm2
+
+    @staticmethod
+    def backward(ctx, dfeat, _):
+        h, tok, lw, pj, ws = ctx.saved_tensors
+        rows, Lt, W = h.shape
+        D = pj.shape[1]
+        dev = h.device
+        dt = L.dtype_code(h.dtype)
+        df = dfeat.detach().to(h.dtype).contiguous()
+        dx_rows = torch.empty(rows, W, dtype=h.dtype, device=dev)
+        dlw = torch.empty(W, dtype=torch.float32, device=dev)
+        dlb = torch.empty(W, dtype=torch.float32, device=dev)
+        dproj = torch.empty(W, D, dtype=torch.float32, device=dev)
+        L.check(L.load().ce_proj_bwd(h.data_ptr(), Lt * W, L.ptr(tok), L.ptr(lw), pj.data_ptr(), df.data_ptr(), rows, W, D, dt,
+                                     dx_rows.data_ptr(), dlw.data_ptr(), dlb.data_ptr(), dproj.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), L.stream_ptr()), "projection backward")
+        dh = None
+        if ctx.needs_input_grad[0]:
+            dh = torch.zeros_like(h)
+            ar = torch.arange(rows, device=dev)
+            dh[ar, tok if tok is not None else torch.zeros_like(ar)] = dx_rows
+        return (dh, None, dlw.to(h.dtype) if ctx.has_ln else None, dlb.to(h.dtype) if ctx.has_ln else None,
+                dproj.to(h.dtype), None)
+
+
+def projection_tail(hidden, proj, ln_weight=None, ln_bias=None, token_index=None, eps=1e-5):
+    """(features [rows, D], squared L2 norms [rows]) = LayerNorm(hidden[arange, token_index]) @ proj.
+    ``token_index`` None = token 0 (the class token, model_clip.py:256); pass ``text.argmax(dim=-1)`` for
+    the text side (model_clip.py:415)."""
+    return _ProjectionTail.apply(hidden, token_index, ln_weight, ln_bias, proj, eps)
+
+
+# --------------------------------------------------------------------------------------------
 # packed (variable-length) node sets: SURVEY.md 8f-3
 # --------------------------------------------------------------------------------------------
 class PackedNodes:

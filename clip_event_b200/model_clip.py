@@ -113,6 +113,38 @@ class ClipEventHead(nn.Module):
                 F_.pack_nodes(text_features, F_.num_mask(entitytxt_num)))
 
 
+class ProjectionTail(nn.Module):
+    """The last step of either encoder, SURVEY.md 8f-2: ``LayerNorm(hidden[arange, token]) @ proj``.
+
+    * image side (model_clip.py:253-260): ``ProjectionTail(width, embed_dim)`` holds ``ln_post`` and ``proj``
+      (initialised as model_clip.py:214-216); call it on the transformer output ``[B, L, width]``.
+    * text side (model_clip.py:412-415): the same module holds ``ln_final`` and ``text_projection``; pass
+      ``token_index=text.argmax(dim=-1)`` (the eot token).  LayerNorm acts per token, so normalising only the
+      selected token equals the reference's ``ln_final(x)[arange, eot]``.
+
+    One row kernel (gather + LayerNorm, fp32 statistics as the reference's LayerNorm subclass,
+    model_clip.py:157-163) feeds the tcgen05 GEMM; the features come back together with their squared L2
+    norms (``self.last_norm2``), which is what ``ClipEventHead`` computes next (model_clip.py:496-497).
+    """
+
+    def __init__(self, width: int, embed_dim: int, layer_norm: bool = True, eps: float = 1e-5):
+        super().__init__()
+        self.eps = eps
+        if layer_norm:
+            self.weight = nn.Parameter(torch.ones(width))
+            self.bias = nn.Parameter(torch.zeros(width))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+        self.proj = nn.Parameter((width ** -0.5) * torch.randn(width, embed_dim))
+        self.last_norm2 = None
+
+    def forward(self, hidden, token_index=None):
+        feat, norm2 = F_.projection_tail(hidden, self.proj, self.weight, self.bias, token_index, self.eps)
+        self.last_norm2 = norm2
+        return feat
+
+
 def _localise_labels(labels_per_image, labels_per_text, b, cols_local, group):
     """The reference's collate_fn numbers rows and columns within ONE rank's batch
     (dataset_voa.py:617-663).  The sharded kernels want labels_per_image as GLOBAL column indices and

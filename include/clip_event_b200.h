@@ -179,6 +179,27 @@ int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* img, int64_t
                   void* dtxt, void* dimg, void* dimg_slot0, void* workspace,
                   size_t workspace_bytes, ce_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SURVEY.md 8f-2 -- the projections that feed the head: image side model_clip.py:253-260
+ * (x[:, 0, :] -> ln_post -> @ proj), text side model_clip.py:412-415 (ln_final -> x[arange, eot] ->
+ * @ text_projection).  hidden: [rows, L, W] last hidden states (sample_stride = L * W elements);
+ * token_index: [rows] int64 token position per sample (NULL = token 0, the class token);
+ * ln_w / ln_b [W] in the I/O dtype (both NULL = no LayerNorm); proj [W, D] row-major in the I/O dtype.
+ * ce_proj_fwd writes feat [rows, D] (I/O dtype) and, if non-NULL, norm2 [rows] = the squared L2 norm of
+ * each stored feature row (model_clip.py:496-497 needs it next).  ce_proj_bwd, called with the SAME
+ * workspace after ce_proj_fwd, returns the gradient of the gathered token rows dx_rows [rows, W] (I/O
+ * dtype; every other token's gradient is zero), dln_w / dln_b [W] fp32 and dproj [W, D] fp32.
+ * W, D multiples of 8; fp32 mode runs the GEMMs as 3xTF32 like the rest of the library.
+ * ------------------------------------------------------------------------------------------ */
+size_t ce_proj_workspace_bytes(int rows, int W, int D, int dtype);
+int ce_proj_fwd(const void* hidden, int64_t sample_stride, const int64_t* token_index, const void* ln_w,
+                const void* ln_b, float eps, const void* proj, int rows, int W, int D, int dtype,
+                void* feat, float* norm2, void* workspace, size_t workspace_bytes, ce_stream_t stream);
+int ce_proj_bwd(const void* hidden, int64_t sample_stride, const int64_t* token_index, const void* ln_w,
+                const void* proj, const void* dfeat, int rows, int W, int D, int dtype, void* dx_rows,
+                float* dln_w, float* dln_b, float* dproj, void* workspace, size_t workspace_bytes,
+                ce_stream_t stream);
+
 /* Packed (variable-length) node sets -- SURVEY.md 8f-3; the reference pads every sample to the batch maximum
  * (model_clip.py:531-552, dataset_voa.py:532-544,566-577) and masks the padding afterwards.  Here the rows of
  * sample b are txt_off[b] .. txt_off[b+1]-1 of a dense [sum_m, D] matrix (img_off likewise, the whole-image slot

@@ -270,6 +270,62 @@ def test_contrastive_parity_with_stored_exponentials_forced():
 
 
 # ------------------------------------------------------------------------------------------
+# the projections that feed the head, against the reference's own tail
+# (model_clip.py:253-260: ln_post(x[:, 0, :]) @ proj ; :412-415: ln_final(x)[arange, eot] @ text_projection)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,Lt,W,D,side", [(64, 50, 768, 512, "image"), (45, 77, 512, 512, "text"), (256, 7, 1024, 768, "image"),
+                                              (33, 5, 264, 136, "text")])
+def test_projection_tail_matches_reference_tail(dtype, rows, Lt, W, D, side):
+    g = torch.Generator().manual_seed(11)
+    hidden = (torch.randn(rows, Lt, W, generator=g) * 1.5 + 0.3).to(dtype)
+    lw = (1.0 + 0.1 * torch.randn(W, generator=g)).to(dtype)
+    lb = (0.1 * torch.randn(W, generator=g)).to(dtype)
+    proj = ((W ** -0.5) * torch.randn(W, D, generator=g)).to(dtype)
+    tok = torch.randint(0, Lt, (rows,), generator=g) if side == "text" else None
+    upstream = torch.randn(rows, D, generator=g).to(dtype)
+    # reference arithmetic (fp64 on the same stored values): LayerNorm in full precision, then the matmul
+    h64, w64, b64, p64 = (t.double().requires_grad_(True) for t in (hidden, lw, lb, proj))
+    sel = h64[torch.arange(rows), tok] if tok is not None else h64[:, 0, :]
+    ref = torch.nn.functional.layer_norm(sel, (W,), w64, b64, 1e-5) @ p64
+    (ref * upstream.double()).sum().backward()
+    tail = ce.ProjectionTail(W, D).cuda().to(dtype)
+    with torch.no_grad():
+        tail.weight.copy_(lw); tail.bias.copy_(lb); tail.proj.copy_(proj)
+    hc = hidden.cuda().requires_grad_(True)
+    feat = tail(hc, None if tok is None else tok.cuda())
+    (feat.float() * upstream.cuda().float()).sum().backward()
+    torch.cuda.synchronize()
+    tol_f, tol_g = (2e-5, 5e-5) if dtype == torch.float32 else (6e-3, 1e-2)   # bf16: the LayerNorm output is rounded once more
+    assert rel_err(feat, ref) < tol_f
+    assert rel_err(tail.last_norm2, feat.float().pow(2).sum(1)) < 1e-5
+    assert rel_err(hc.grad, h64.grad) < tol_g
+    assert rel_err(tail.proj.grad, p64.grad) < tol_g
+    assert rel_err(tail.weight.grad, w64.grad) < tol_g and rel_err(tail.bias.grad, b64.grad) < tol_g
+    # every other token's gradient is exactly zero
+    mask = torch.ones(rows, Lt, dtype=torch.bool)
+    mask[torch.arange(rows), tok if tok is not None else torch.zeros(rows, dtype=torch.long)] = False
+    assert float(hc.grad.cpu()[mask].abs().max()) == 0.0
+
+
+def test_projection_tail_feeds_the_head():
+    """encoder tail -> head -> criterion in one graph: gradients reach the projection and the hidden states."""
+    torch.manual_seed(3)
+    B, T, W, D = 48, 5, 256, 128
+    img_tail, txt_tail = ce.ProjectionTail(W, D).cuda().bfloat16(), ce.ProjectionTail(W, D).cuda().bfloat16()
+    head = ce.ClipEventHead().cuda()
+    hi = torch.randn(B, 10, W, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    ht = torch.randn(B * T, 12, W, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    eot = torch.randint(0, 12, (B * T,), device="cuda")
+    lpi, lpt, idx = syn.contrastive_labels(B, T)
+    lpi_, lpt_ = head(img_tail(hi), txt_tail(ht, eot))
+    ld = ce.CriterionContrastive("ce")(lpi_, lpt_, lpi.cuda(), lpt.cuda(), index_pos=idx.cuda())
+    sum(ld.values()).backward()
+    for t in (hi.grad, ht.grad, img_tail.proj.grad, txt_tail.proj.grad, img_tail.weight.grad, head.logit_scale.grad):
+        assert t is not None and torch.isfinite(t.float()).all() and float(t.float().abs().sum()) > 0
+
+
+# ------------------------------------------------------------------------------------------
 # SURVEY 8f-3: packed (variable-length) node sets -- same numbers as the padded, masked batch
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,M,N,D,masks", [(64, 16, 50, 512, "ragged"), (37, 9, 64, 256, "ragged"), (130, 16, 50, 512, "edge"),
