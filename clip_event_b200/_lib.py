@@ -46,6 +46,8 @@ SIGNATURES = {
     "ce_proj_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ce_proj_fwd": (_i, [_vp, _i64, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "ce_proj_bwd": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ce_p2p_gather": (_i, [_vp, _i, _i64, _vp, _vp]),
+    "ce_p2p_reduce_f32": (_i, [_vp, _i, _i64, _i64, _vp, _i64, _i, _vp, _vp]),
     "ce_head_param_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _f, _f, _f, _f, _f, _vp, _vp]),
     "ce_debug_launch_count": (C.c_ulonglong, []),
     "ce_debug_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -1,4 +1,5 @@
 // Library-wide plumbing: version, thread-local error string, device check, TMA descriptor factory.
+#include <algorithm>
 #include <stdarg.h>
 #include <string.h>
 
@@ -96,6 +97,79 @@ int make_tmap(CUtensorMap* out, const void* ptr, bool fp32, uint64_t inner, uint
 }
 
 }  // namespace ce
+
+// ------------------------------------------------------------------------------------------
+// Device-side exchange over peer memory (NVLink / NVSwitch): the sharded loss head's all-gathers and its
+// gradient reduce-scatter as plain loads from the peers' symmetric buffers -- utils.py:192-206 without a
+// collective library in the data path.  The caller provides the peers' buffer addresses (same layout on
+// every rank) and orders the steps with its own barrier (torch symmetric memory: hdl.barrier()).
+// ------------------------------------------------------------------------------------------
+namespace ce {
+namespace {
+constexpr int kMaxPeers = 16;
+struct PeerPtrs { const void* p[kMaxPeers]; };
+
+__global__ void p2p_gather_kernel(PeerPtrs pp, int world, int64_t vec_each, uint4* dst) {
+  const int64_t total = vec_each * world;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vec_each);
+    dst[i] = reinterpret_cast<const uint4*>(pp.p[r])[i - r * vec_each];
+  }
+}
+// dst[i] = sum_r peer_r[offset + i] (fixed order r = 0..world-1: every rank forms the same bits), 16 bytes per thread;
+// tail: tail_dst[j] = sum_r peer_r[tail_offset + j] for a few scalars riding in the same buffer
+__global__ void p2p_reduce_kernel(PeerPtrs pp, int world, int64_t offset, int64_t n4, float4* dst, int64_t tail_offset,
+                                  int tail_n, float* tail_dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; ++r) {
+      const float4 v = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp.p[r]) + offset)[i];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    dst[i] = s;
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail_n) {
+    float s = 0.f;
+    for (int r = 0; r < world; ++r) s += reinterpret_cast<const float*>(pp.p[r])[tail_offset + threadIdx.x];
+    tail_dst[threadIdx.x] = s;
+  }
+}
+int peer_ptrs(const int64_t* host_ptrs, int world, PeerPtrs* out) {
+  if (world < 1 || world > kMaxPeers) return fail(CE_ERR_ARG, "p2p: world size %d outside 1..%d", world, kMaxPeers);
+  for (int r = 0; r < world; ++r) {
+    if (host_ptrs[r] == 0 || (host_ptrs[r] & 15)) return fail(CE_ERR_ALIGN, "p2p: peer buffer %d is null or not 16-byte aligned", r);
+    out->p[r] = reinterpret_cast<const void*>(host_ptrs[r]);
+  }
+  return CE_OK;
+}
+}  // namespace
+}  // namespace ce
+
+extern "C" int ce_p2p_gather(const int64_t* peer_ptrs_host, int world, int64_t bytes_each, void* dst, ce_stream_t stream) {
+  CE_TRY(ce::check_device());
+  ce::PeerPtrs pp{};
+  CE_TRY(ce::peer_ptrs(peer_ptrs_host, world, &pp));
+  if (bytes_each <= 0 || bytes_each % 16 || ((uintptr_t)dst & 15)) return ce::fail(CE_ERR_ALIGN, "p2p gather: sizes and pointers must be multiples of 16 bytes");
+  const int64_t vec = bytes_each / 16;
+  const int blocks = (int)std::min<int64_t>((vec * world + 255) / 256, 148 * 8);
+  ce::p2p_gather_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pp, world, vec, reinterpret_cast<uint4*>(dst));
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}
+
+extern "C" int ce_p2p_reduce_f32(const int64_t* peer_ptrs_host, int world, int64_t offset_elems, int64_t n, float* dst,
+                                 int64_t tail_offset_elems, int tail_n, float* tail_dst, ce_stream_t stream) {
+  CE_TRY(ce::check_device());
+  ce::PeerPtrs pp{};
+  CE_TRY(ce::peer_ptrs(peer_ptrs_host, world, &pp));
+  if (n <= 0 || n % 4 || offset_elems % 4 || ((uintptr_t)dst & 15)) return ce::fail(CE_ERR_ALIGN, "p2p reduce: n and offset must be multiples of 4 floats");
+  if (tail_n < 0 || tail_n > 32 || (tail_n > 0 && tail_dst == nullptr)) return ce::fail(CE_ERR_ARG, "p2p reduce: bad tail");
+  const int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256, 148 * 8);
+  ce::p2p_reduce_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pp, world, offset_elems, n / 4, reinterpret_cast<float4*>(dst),
+                                                                               tail_offset_elems, tail_n, tail_dst);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}
 
 extern "C" int ce_version(void) { return 100; }
 extern "C" const char* ce_last_error(void) { return ce::g_err; }

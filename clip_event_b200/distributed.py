@@ -62,11 +62,11 @@ class CudaBackend:
         return out[0], out[1]
 
     def bwd_partial(self, img_all, txt, ls, labels_i_all, labels_t, index_pos, col_offset, g_i, g_t,
-                    R_total, P_total, state):
+                    R_total, P_total, state, dimg_out=None, dls_out=None):
         ws, R, C, P, D, dt = state
         dtxt = torch.empty_like(txt)
-        dimg_hat = torch.empty(R, D, dtype=torch.float32, device=txt.device)
-        dls = torch.empty(1, dtype=torch.float32, device=txt.device)
+        dimg_hat = dimg_out if dimg_out is not None else torch.empty(R, D, dtype=torch.float32, device=txt.device)
+        dls = dls_out if dls_out is not None else torch.empty(1, dtype=torch.float32, device=txt.device)
         L.check(self.lib.ce_contrastive_bwd_partial(
             img_all.data_ptr(), txt.data_ptr(), ls.data_ptr(), labels_i_all.data_ptr(), labels_t.data_ptr(),
             index_pos.data_ptr(), R, C, P, D, int(col_offset), L.CE_IMG_CE_OVERBATCH, 1, 0, dt,
@@ -121,6 +121,131 @@ def _reduce_scatter_sums(pairs, rank, group):
             dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
 
 
+# --------------------------------------------------------------------------------------------
+# exchange steps: NCCL collectives, or loads from the peers' symmetric buffers over NVLink
+# --------------------------------------------------------------------------------------------
+class NcclExchange:
+    """The three exchange steps of the sharded loss head as collectives of the process group (NCCL; gloo in
+    the CPU tests)."""
+
+    def __init__(self, group):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def gather_rows(self, x):
+        out = torch.empty(self.world * x.numel(), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.reshape(-1), group=self.group)
+        return out
+
+    def gather_stats(self, stats):
+        out = torch.empty(self.world * stats.numel(), dtype=torch.float32, device=stats.device)
+        dist.all_gather_into_tensor(out, stats, group=self.group)
+        return out.view(self.world, stats.numel())
+
+    def grad_buffers(self, R, D, device):
+        return None, None
+
+    def reduce_scatter(self, dimg_hat, dls, b):
+        mine = torch.empty(b, dimg_hat.shape[1], dtype=torch.float32, device=dimg_hat.device)
+        dls_tot = torch.empty(1, dtype=torch.float32, device=dimg_hat.device)
+        _reduce_scatter_sums([(mine, dimg_hat), (dls_tot, dls.expand(self.world).contiguous())], self.rank, self.group)
+        return mine, dls_tot
+
+
+class SymmExchange:
+    """The same three steps without a collective library in the data path: every rank keeps its contribution in a
+    symmetric-memory buffer (torch.distributed._symmetric_memory: one allocation mapped into every peer), a
+    cross-rank barrier orders the step, and a copy / reduce kernel of this library reads the peers' buffers
+    over NVLink (``ce_p2p_gather`` / ``ce_p2p_reduce_f32``).  The gradient GEMMs write their partial d I^
+    straight into the symmetric buffer; the reduce-scatter is one kernel that sums this rank's rows over the
+    peers in rank order.  Buffers are created (a collective rendezvous) on first use per shape and reused.
+
+    Ordering: a buffer written in step n+1 was last read by the peers before their next barrier arrival, which
+    precedes this rank passing that barrier -- three barriers per step keep writers behind readers."""
+
+    _CACHE = {}
+
+    def __init__(self, group):
+        import torch.distributed._symmetric_memory as symm
+        self.symm = symm
+        self.group = dist.group.WORLD if group is None else group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.lib = L.load()
+
+    def _buf(self, tag, numel, dtype, device):
+        key = (id(self.group), tag, int(numel), dtype, str(device))
+        hit = SymmExchange._CACHE.get(key)
+        if hit is None:
+            t = self.symm.empty(int(numel), dtype=dtype, device=device)
+            h = self.symm.rendezvous(t, self.group)
+            import ctypes
+            ptrs = (ctypes.c_int64 * self.world)(*[int(p) for p in h.buffer_ptrs])
+            hit = SymmExchange._CACHE[key] = (t, h, ptrs)
+        return hit
+
+    def _gather(self, tag, x):
+        flat = x.reshape(-1)
+        n = flat.numel()
+        pad = (-n * flat.element_size()) % 16 // flat.element_size()
+        t, h, ptrs = self._buf(tag, n + pad, flat.dtype, flat.device)
+        t[:n].copy_(flat)
+        h.barrier(channel=0)
+        out = torch.empty(self.world * (n + pad), dtype=flat.dtype, device=flat.device)
+        L.check(self.lib.ce_p2p_gather(ptrs, self.world, (n + pad) * flat.element_size(), out.data_ptr(), L.stream_ptr()),
+                "p2p gather")
+        return out.view(self.world, n + pad)[:, :n]
+
+    def gather_rows(self, x):
+        return self._gather("img", x).reshape(-1)
+
+    def gather_stats(self, stats):
+        return self._gather("stats", stats)
+
+    def grad_buffers(self, R, D, device):
+        """[R, D] fp32 partial gradient + one slot for dlogit_scale, both inside this rank's symmetric buffer."""
+        t, _, _ = self._buf("dimg", R * D + 16, torch.float32, device)
+        return t[: R * D].view(R, D), t[R * D: R * D + 1]
+
+    def reduce_scatter(self, dimg_hat, dls, b):
+        R, D = dimg_hat.shape
+        t, h, ptrs = self._buf("dimg", R * D + 16, torch.float32, dimg_hat.device)
+        if dimg_hat.data_ptr() != t.data_ptr():      # the caller did not use grad_buffers()
+            t[: R * D].copy_(dimg_hat.reshape(-1))
+            t[R * D: R * D + 1].copy_(dls.reshape(1))
+        h.barrier(channel=0)
+        mine = torch.empty(b, D, dtype=torch.float32, device=dimg_hat.device)
+        dls_tot = torch.empty(1, dtype=torch.float32, device=dimg_hat.device)
+        L.check(self.lib.ce_p2p_reduce_f32(ptrs, self.world, self.rank * b * D, b * D, mine.data_ptr(), R * D, 1,
+                                           dls_tot.data_ptr(), L.stream_ptr()), "p2p reduce")
+        return mine, dls_tot
+
+
+_EXCHANGES = {}
+
+
+def make_exchange(group, device):
+    """Symmetric-memory exchange on CUDA when torch offers it (``CE_DIST_EXCHANGE=nccl`` forces the collectives),
+    NCCL / gloo collectives otherwise."""
+    import os
+    key = (id(group), str(device))
+    ex = _EXCHANGES.get(key)
+    if ex is None:
+        want = os.environ.get("CE_DIST_EXCHANGE", "symm")
+        ex = None
+        if want != "nccl" and torch.device(device).type == "cuda" and dist.get_backend(group) == "nccl" and dist.get_world_size(group) <= 16:
+            try:
+                ex = SymmExchange(group)
+                ex._buf("probe", 4, torch.float32, device)        # a collective: every rank takes the same branch or none
+            except Exception:
+                ex = None
+        if ex is None:
+            ex = NcclExchange(group)
+        _EXCHANGES[key] = ex
+    return ex
+
+
 _CANONICAL = {}
 
 
@@ -147,9 +272,8 @@ class _GlobalContrastive(torch.autograd.Function):
         b, D = img_c.shape
         C = txt_c.shape[0]
         # 1. gather images and their labels (texts stay local)
-        img_all = torch.empty(world * b * D, dtype=img_c.dtype, device=dev)
-        dist.all_gather_into_tensor(img_all, img_c.view(-1), group=group)
-        img_all = img_all.view(world * b, D)
+        ex = make_exchange(group, dev)
+        img_all = ex.gather_rows(img_c).view(world * b, D)
         if labels_i is None:
             # canonical contract (dataset_voa.py:617-621): image r's positive is column r*T -- no exchange
             lab_all = _canonical_labels(world * b, C // b, dev)
@@ -160,11 +284,10 @@ class _GlobalContrastive(torch.autograd.Function):
         col_offset = rank * C
         stats, state = compute.fwd_partial(img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset)
         # 3. exchange the statistics: one record [row_part (R x 4) | sums (4)] per rank
-        stats_all = torch.empty(world * stats.numel(), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(stats_all, stats, group=group)
-        stats_all = stats_all.view(world, stats.numel())
+        stats_all = ex.gather_stats(stats).contiguous()
         loss_i, loss_t = compute.fwd_finish(stats_all, world, state)
         ctx.saved = (img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset, state)
+        ctx.ex = ex
         ctx.meta = (group, compute, world, rank, b, logit_scale.dtype, logit_scale.shape, bool(ddp_average))
         return loss_i, loss_t
 
@@ -187,13 +310,14 @@ class _GlobalContrastive(torch.autograd.Function):
             gi, gt = gi * world, gt * world
         R_total = img_all.shape[0]
         P_total = index_pos.numel() * world   # ranks hold equal shards
+        ex = ctx.ex
+        dimg_buf, dls_buf = ex.grad_buffers(R_total, img_all.shape[1], dev)
+        extra = () if dimg_buf is None else (dimg_buf, dls_buf)
         dtxt, dimg_hat, dls = compute.bwd_partial(img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset,
-                                                  gi, gt, R_total, P_total, state)
-        # gradient return: reduce-scatter of s G T^_local, with the dlogit_scale partials riding in the
-        # same NCCL launch (every rank contributes its partial to every chunk of a [world] vector)
-        mine = torch.empty(b, dimg_hat.shape[1], dtype=torch.float32, device=dev)
-        dls_tot = torch.empty(1, dtype=torch.float32, device=dev)
-        _reduce_scatter_sums([(mine, dimg_hat), (dls_tot, dls.expand(world).contiguous())], rank, group)
+                                                  gi, gt, R_total, P_total, state, *extra)
+        # gradient return: reduce-scatter of s G T^_local with the dlogit_scale partials riding along (one NCCL
+        # launch, or one kernel over the peers' symmetric buffers)
+        mine, dls_tot = ex.reduce_scatter(dimg_hat, dls, b)
         if ddp_average:
             dls_tot = dls_tot / world
         dimg = compute.bwd_finish(img_all[rank * b:(rank + 1) * b], mine)
@@ -277,9 +401,8 @@ class _GlobalLossHeadStep(torch.autograd.Function):
         else:
             loss_ot_local, detxt, dobj, keep = ot_eager(etxt_c, obj_c, tnum, onum, need_o, 0)
         # 1. gather the images
-        img_all = torch.empty(world * b * D, dtype=img_c.dtype, device=dev)
-        dist.all_gather_into_tensor(img_all, img_c.view(-1), group=group)
-        img_all = img_all.view(world * b, D)
+        ex = make_exchange(group, dev)
+        img_all = ex.gather_rows(img_c).view(world * b, D)
         if labels_i is None:
             lab_all = _canonical_labels(world * b, C // b, dev)
         else:
@@ -293,9 +416,7 @@ class _GlobalLossHeadStep(torch.autograd.Function):
         if cuda:
             cur.wait_event(ot_done)
         stats[R * 4 + 2:R * 4 + 3].copy_(loss_ot_local.reshape(1).to(torch.float32))
-        stats_all = torch.empty(world * stats.numel(), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(stats_all, stats, group=group)
-        stats_all = stats_all.view(world, stats.numel())
+        stats_all = ex.gather_stats(stats).contiguous()
         loss_i, loss_t = compute.fwd_finish(stats_all, world, state)
         loss_ot = stats_all[:, R * 4 + 2].sum()
         # 4. gradients of (loss_i + loss_t) for unit upstream gradients
@@ -303,11 +424,11 @@ class _GlobalLossHeadStep(torch.autograd.Function):
         if need_c:
             one = torch.ones(1, dtype=torch.float32, device=dev)
             g = one * world if ddp_average else one
+            dimg_buf, dls_buf = ex.grad_buffers(R, D, dev)
+            extra = () if dimg_buf is None else (dimg_buf, dls_buf)
             dtxt, dimg_hat, dls = compute.bwd_partial(img_all, txt_c, ls, lab_all, labels_t, index_pos, col_offset,
-                                                      g, g, R, index_pos.numel() * world, state)
-            mine = torch.empty(b, D, dtype=torch.float32, device=dev)
-            dls_tot = torch.empty(1, dtype=torch.float32, device=dev)
-            _reduce_scatter_sums([(mine, dimg_hat), (dls_tot, dls.expand(world).contiguous())], rank, group)
+                                                      g, g, R, index_pos.numel() * world, state, *extra)
+            mine, dls_tot = ex.reduce_scatter(dimg_hat, dls, b)
             if ddp_average:
                 dls_tot = dls_tot / world
             dimg = compute.bwd_finish(img_all[rank * b:(rank + 1) * b], mine)

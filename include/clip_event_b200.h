@@ -200,6 +200,21 @@ int ce_proj_bwd(const void* hidden, int64_t sample_stride, const int64_t* token_
                 float* dln_w, float* dln_b, float* dproj, void* workspace, size_t workspace_bytes,
                 ce_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Device-side exchange for the sharded loss head (what utils.py:192-206 gathers, and the gradient return),
+ * as plain loads from the peers' buffers over NVLink / NVSwitch -- no collective library in the data path.
+ * peer_ptrs_host: HOST array of `world` device addresses, one per rank, of buffers with the same layout on
+ * every rank (torch symmetric memory: hdl.buffer_ptrs).  The caller orders the steps with its own cross-rank
+ * barrier (hdl.barrier()) before the call and before the buffers are overwritten.
+ *   ce_p2p_gather     dst[r * bytes_each ...] = peer r's first bytes_each bytes            (all-gather)
+ *   ce_p2p_reduce_f32 dst[i] = sum_r peer_r[offset_elems + i], i < n, summed in rank order (reduce-scatter:
+ *                     offset = this rank's slice); tail_dst[j] = sum_r peer_r[tail_offset_elems + j], j < tail_n <= 32
+ * Sizes / offsets in multiples of 16 bytes; world <= 16.
+ * ------------------------------------------------------------------------------------------ */
+int ce_p2p_gather(const int64_t* peer_ptrs_host, int world, int64_t bytes_each, void* dst, ce_stream_t stream);
+int ce_p2p_reduce_f32(const int64_t* peer_ptrs_host, int world, int64_t offset_elems, int64_t n, float* dst,
+                      int64_t tail_offset_elems, int tail_n, float* tail_dst, ce_stream_t stream);
+
 /* Packed (variable-length) node sets -- SURVEY.md 8f-3; the reference pads every sample to the batch maximum
  * (model_clip.py:531-552, dataset_voa.py:532-544,566-577) and masks the padding afterwards.  Here the rows of
  * sample b are txt_off[b] .. txt_off[b+1]-1 of a dense [sum_m, D] matrix (img_off likewise, the whole-image slot
