@@ -16,7 +16,7 @@ timeout 120 python tools/ot_tune.py c3 bf16 > gpurun_out/${R}_ot_tune_c3.log 2>&
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:ot_stream" -s 32 -c 1 \
     -o gpurun_out/prof_${R}_ot_stream python tools/ot_tune.py c3 bf16 > gpurun_out/${R}_ncu_ot.log 2>&1
 timeout 120 python tools/con_tune.py c3 bf16 > gpurun_out/${R}_con_tune_c3.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:umma_gemm" -s 24 -c 8 \
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:umma_gemm|bwd_|normalize_bwd|prep_all|fwd_items" -s 100 -c 20 \
     -o gpurun_out/prof_${R}_gemm_chain python tools/con_tune.py c3 bf16 > gpurun_out/${R}_ncu_gemm.log 2>&1
 timeout 120 python tools/ot_tune.py c4 bf16 > gpurun_out/${R}_ot_tune_c4.log 2>&1
 timeout 300 python bench.py --workload c4 --steps 20 --warmup 5 --no-cpu-baseline --no-secondary > gpurun_out/${R}_bench_c4.json 2> gpurun_out/${R}_bench_c4.err
