@@ -14,7 +14,11 @@
  *     including workspaces (sizes from the *_workspace_bytes queries); the library never allocates
  *     device memory; its only state is a thread-local error string, the launch counter behind
  *     ce_debug_launch_count() and a few debug switches read once from the environment
- *     (CE_GEMM_PAIR, CE_OT_FUSED, CE_OT_POLL, CE_OT_TRACE_PTR -- tuning aids, not configuration);
+ *     (CE_GEMM_PAIR, CE_CTR_STORED, CE_OT_STREAM, CE_OT_FUSED, CE_OT_PARKS / CE_OT_CY / CE_OT_GY, CE_OT_TRACE_PTR --
+ *     tuning aids, not configuration);
+ *   - inputs are assumed finite: the streaming OT kernel re-uses its shared-memory row buffers from sample to
+ *     sample and multiplies rows that are not loaded for a sample (padding beyond the node count) by exact
+ *     zeros, so a NaN / Inf in one sample can surface in the next sample handled by the same thread block;
  *   - tensors are row-major and contiguous unless a stride argument says otherwise; embedding
  *     pointers must be 16-byte aligned and D a multiple of 8;
  *   - dtype: CE_F32 = fp32 in / fp32 out, tensor-core products as 3xTF32 (fp32-level accuracy);
