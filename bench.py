@@ -14,7 +14,7 @@ backward of the whole loss head over one synthetic batch:
   * ``roofline``  for the dominant kernel chain, from CUDA-event timings taken in this run;
   * ``cpu_baseline`` the oracle (reference algorithm, PyTorch CPU) on a bounded sample, rank 0, N=1.
 Multi-GPU (torchrun): strong scaling -- the GLOBAL batch of the workload is sharded over the ranks;
-every rank scores against the global negative set (all-gather / reduce-scatter over NCCL).
+every rank scores against the global negative set (device-side gather / reduce over symmetric memory; NCCL collectives as the fallback).
 """
 import argparse
 import json
@@ -612,6 +612,13 @@ def main():
             "roofline": dominant, "roofline_secondary": secondary,
             "losses": [float(x) for x in losses_host.tolist()],
         }
+        if world > 1:
+            from clip_event_b200 import distributed as _cd
+            kinds = sorted({type(e).__name__ for e in _cd._EXCHANGES.values()})
+            out["timing"]["exchange"] = {"SymmExchange": "device-side: barrier + loads from the peers' symmetric buffers over NVLink "
+                                                         "(ce_p2p_gather / ce_p2p_reduce_f32), three steps per training step",
+                                         "NcclExchange": "NCCL: all-gather, all-gather, one coalesced reduce-scatter"}.get(
+                                             kinds[0] if kinds else "", "none")
         if cpu is not None:
             out["cpu_baseline"] = cpu
         if extra is not None:
