@@ -30,7 +30,8 @@ namespace {
 constexpr int kCH = 16;                // rows per chunk
 constexpr int kMP = 16;                // text nodes padded to one m16 / two n8 tiles
 constexpr int kNR = 64;                // image-node rows covered by the solver warp
-constexpr int kSLd = 20;               // floats per row of the S tile (conflict-free LDS.128)
+constexpr int kSLd = 16;               // floats per row of the S tile: dense 64-byte rows, the 16-byte chunk index is
+                                       // XOR-swizzled with (row >> 1) & 3 (conflict-free LDS.128 by row, 1 KB per park saved)
 constexpr int kWLd = 24;               // bf16 per row of the W tile (48 B: conflict-free ldmatrix)
 constexpr int kPLd = 18;               // floats per lane row of the column-sum transpose
 constexpr int kMaxParks = 6;
@@ -407,20 +408,24 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
       if (j == 0) OT_TRACE(k, 5);
       ParkScratch& sc = scr[park];
       if (hasA) {
-        float* Sp = sc.S + (cA * kCH + g) * kSLd + 2 * t;
+        float* Sp = sc.S + (cA * kCH + g) * kSLd + 2 * (t & 1);
+        const int swg = (g >> 1) & 3;                    // the same key for rows g and g + 8
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          *reinterpret_cast<float2*>(Sp + 8 * i) = make_float2(accA[i][0], accA[i][1]);
-          *reinterpret_cast<float2*>(Sp + 8 * kSLd + 8 * i) = make_float2(accA[i][2], accA[i][3]);
+          const int ch = ((2 * i + (t >> 1)) ^ swg) * 4;   // columns 8 i + 2 t, + 1 live in chunk 2 i + t / 2
+          *reinterpret_cast<float2*>(Sp + ch) = make_float2(accA[i][0], accA[i][1]);
+          *reinterpret_cast<float2*>(Sp + 8 * kSLd + ch) = make_float2(accA[i][2], accA[i][3]);
         }
         if (diag) { sc.yn2[cA * kCH + g] = (g & 1) ? gA[0][1] : gA[0][0]; sc.yn2[cA * kCH + g + 8] = (g & 1) ? gA[1][3] : gA[1][2]; }
       }
       if (hasB) {
-        float* Sp = sc.S + (cB * kCH + g) * kSLd + 2 * t;
+        float* Sp = sc.S + (cB * kCH + g) * kSLd + 2 * (t & 1);
+        const int swg = (g >> 1) & 3;                    // the same key for rows g and g + 8
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          *reinterpret_cast<float2*>(Sp + 8 * i) = make_float2(accB[i][0], accB[i][1]);
-          *reinterpret_cast<float2*>(Sp + 8 * kSLd + 8 * i) = make_float2(accB[i][2], accB[i][3]);
+          const int ch = ((2 * i + (t >> 1)) ^ swg) * 4;   // columns 8 i + 2 t, + 1 live in chunk 2 i + t / 2
+          *reinterpret_cast<float2*>(Sp + ch) = make_float2(accB[i][0], accB[i][1]);
+          *reinterpret_cast<float2*>(Sp + 8 * kSLd + ch) = make_float2(accB[i][2], accB[i][3]);
         }
         if (diag) { sc.yn2[cB * kCH + g] = (g & 1) ? gB[0][1] : gB[0][0]; sc.yn2[cB * kCH + g + 8] = (g & 1) ? gB[1][3] : gB[1][2]; }
       }
@@ -457,6 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
       // column c of the 16 rows held by this half-warp's lanes; the upper half walks the rows 8 ahead so
       // that the two halves hit disjoint banks (18 * 8 = 16 mod 32)
       const float* pcol = sc.P + (lane >> 4) * 16 * kPLd + c;
+      const int ssw = (lane >> 1) & 3;                    // S tile swizzle key of rows lane and lane + 32
       const int prot = (lane >> 4) * 8;
 
       role_wait(&bars->s_ready[park], ((k / P) & 1), lane, sleep_ns);
@@ -474,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
         const float4* xn = reinterpret_cast<const float4*>(sc.v);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 u0 = s0[q], u1 = s1[q], x4 = xn[q];
+          const float4 u0 = s0[q ^ ssw], u1 = s1[q ^ ssw], x4 = xn[q];
           const float sv0[4] = {u0.x, u0.y, u0.z, u0.w}, sv1[4] = {u1.x, u1.y, u1.z, u1.w};
           const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
           float a0[4], a1[4];
@@ -609,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) ot_stream_kernel(const OtFusedArg
         const float4* vp = reinterpret_cast<const float4*>(sc.v);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 u40 = s0[q], u41 = s1[q], x4 = xn[q], v4 = vp[q];
+          const float4 u40 = s0[q ^ ssw], u41 = s1[q ^ ssw], x4 = xn[q], v4 = vp[q];
           const float sv0[4] = {u40.x, u40.y, u40.z, u40.w}, sv1[4] = {u41.x, u41.y, u41.z, u41.w};
           const float xx[4] = {x4.x, x4.y, x4.z, x4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
           const float r0[4] = {R0[2 * q].x, R0[2 * q].y, R0[2 * q + 1].x, R0[2 * q + 1].y};
