@@ -143,6 +143,27 @@ int peer_ptrs(const int64_t* host_ptrs, int world, PeerPtrs* out) {
   return CE_OK;
 }
 }  // namespace
+// 3-D tensor map over a batch of row-major [rows, inner] bf16 matrices (batch stride in elements), 128-byte
+// swizzle, out-of-bounds rows / samples read as zeros and are clipped on stores (csrc/ot_wide.cu).
+int make_tmap3d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch,
+                     uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(CE_ERR_ARCH, "cuTensorMapEncodeTiled is not available from this driver");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_elems * 2) % 16 || (batch_stride_elems * 2) % 16)
+    return fail(CE_ERR_ALIGN, "TMA operand must be 16-byte aligned with 16-byte multiple strides");
+  cuuint64_t dims[3] = {inner, rows, batch};
+  cuuint64_t strides[2] = {row_stride_elems * 2, batch_stride_elems * 2};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CE_ERR_ARG, "cuTensorMapEncodeTiled (3-D) failed (%d) inner=%llu rows=%llu batch=%llu box=%ux%u", (int)r,
+                (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)batch, box_inner, box_rows);
+  return CE_OK;
+}
+
 }  // namespace ce
 
 extern "C" int ce_p2p_gather(const int64_t* peer_ptrs_host, int world, int64_t bytes_each, void* dst, ce_stream_t stream) {

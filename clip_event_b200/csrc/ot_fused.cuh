@@ -45,4 +45,20 @@ bool ot_stream_supported(int M, int N, int D, int dtype);
 size_t ot_stream_smem_bytes(int D, int parks, int cy_depth, int gy_depth);
 int launch_ot_stream(OtFusedArgs a, cudaStream_t st);
 
+// Gradient contraction for the plans the streaming kernel does not take (csrc/ot_wide.cu): bf16, D a multiple of 64.
+// TMA-fed persistent kernel; W / ax / ay are the solver's outputs (ot_ipot_kernel), dx_acc the fp32 accumulator
+// of samples whose image rows are split over several CTAs (ot_wide_nsplit > 1).
+struct OtWideGradArgs {
+  const void* txt; const void* img;
+  int64_t txt_bs, img_bs;
+  int B, M, N, D;
+  const float* W; const float* ax; const float* ay;
+  int Nld;
+  void* dtxt; void* dimg;
+  float* dx_acc;
+};
+bool ot_wide_supported(int M, int N, int D, int dtype);
+int ot_wide_nsplit(int M, int N, int D);
+int launch_ot_wide_grad(const OtWideGradArgs& g, cudaStream_t st);
+
 }  // namespace ce

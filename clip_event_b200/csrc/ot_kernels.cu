@@ -1321,7 +1321,7 @@ extern "C" size_t ce_ot_workspace_bytes(int B, int M, int N, int D) {
   bytes += align_up(sizeof(float) * (size_t)B * p.MP, 256);           // nx2 / ax
   bytes += align_up(sizeof(float) * (size_t)B * Nld, 256);            // ny2 / ay
   bytes += align_up(sizeof(float) * (size_t)B * 2 * N * p.MP, 256);   // big-shape solver scratch
-  if (p.nsplit > 1) bytes += align_up(sizeof(float) * (size_t)B * M * D, 256);  // dx accumulators
+  if (p.nsplit > 1 || ot_wide_nsplit(M, N, D) > 1) bytes += align_up(sizeof(float) * (size_t)B * M * D, 256);  // dx accumulators
   return bytes + 1024;
 }
 
@@ -1383,7 +1383,10 @@ extern "C" int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* i
   a.ny2 = cv.take<float>((size_t)B * Nld);
   float* scratch = cv.take<float>((size_t)B * 2 * N * p.MP);
   a.Nld = Nld; a.dtxt = dtxt; a.dimg = dimg; a.nsplit = p.nsplit;
-  a.dx_acc = p.nsplit > 1 ? cv.take<float>((size_t)B * M * D) : nullptr;
+  // bf16 gradients of these plans: the TMA-fed kernel of csrc/ot_wide.cu (CE_OT_WIDE=0: the mma.sync predecessor)
+  const bool wide_grad = dtxt != nullptr && ot_wide_supported(M, N, D, dtype);
+  const int grad_nsplit = wide_grad ? ot_wide_nsplit(M, N, D) : p.nsplit;
+  a.dx_acc = (p.nsplit > 1 || grad_nsplit > 1) ? cv.take<float>((size_t)B * M * D) : nullptr;
 
   if (dtype == CE_F32) CE_TRY(dispatch_mp<CE_F32>(false, a, p, st));
   else CE_TRY(dispatch_mp<CE_BF16>(false, a, p, st));
@@ -1407,10 +1410,16 @@ extern "C" int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* i
   CE_LAUNCH_CHECK();
 
   if (dtxt != nullptr) {
-    if (p.nsplit > 1) CE_CUDA_TRY(cudaMemsetAsync(a.dx_acc, 0, sizeof(float) * (size_t)B * M * D, st));
-    if (dtype == CE_F32) CE_TRY(dispatch_mp<CE_F32>(true, a, p, st));
+    if (grad_nsplit > 1) CE_CUDA_TRY(cudaMemsetAsync(a.dx_acc, 0, sizeof(float) * (size_t)B * M * D, st));
+    if (wide_grad) {
+      OtWideGradArgs wg{};
+      wg.txt = txt; wg.img = img; wg.txt_bs = txt_bstride; wg.img_bs = img_bstride;
+      wg.B = B; wg.M = M; wg.N = N; wg.D = D; wg.W = a.S; wg.ax = a.nx2; wg.ay = a.ny2; wg.Nld = Nld;
+      wg.dtxt = dtxt; wg.dimg = dimg; wg.dx_acc = a.dx_acc;
+      CE_TRY(launch_ot_wide_grad(wg, st));
+    } else if (dtype == CE_F32) CE_TRY(dispatch_mp<CE_F32>(true, a, p, st));
     else CE_TRY(dispatch_mp<CE_BF16>(true, a, p, st));
-    if (p.nsplit > 1) {
+    if (grad_nsplit > 1) {
       int blocks = (int)std::min<int64_t>(((int64_t)B * M * D + 255) / 256, 148 * 8);
       if (dtype == CE_F32) ot_dx_finish_kernel<CE_F32><<<blocks, 256, 0, st>>>(a, p.MP);
       else ot_dx_finish_kernel<CE_BF16><<<blocks, 256, 0, st>>>(a, p.MP);

@@ -1,0 +1,447 @@
+// OT gradient contraction for plans too large for the streaming kernel (bf16; c4: 32 x 257 x 768, the c5
+// sweep): dy = -W^t x + ay*y, dx = -W y + ax*x  (model_ot.py:81-83 -- IPOT is not
+// differentiated through, so the plan W enters as a constant).
+//
+// HBM-bound by construction: x, y are read once and dx, dy written once, 2 (M+N) D e bytes per sample; the
+// contraction is 32 MACs per output element, so the kernel is written around its instruction count
+// (the mma.sync predecessor `ot_grad_kernel` issued 15 instructions per MMA: 4-byte fragment loads, 4-byte
+// global stores with their address arithmetic, 16-byte cp.async per thread).  Here
+//   * persistent CTAs walk (sample, row split, column range) items; 64-column slabs of [x rows | y rows] arrive
+//     through a 3-stage ring by TMA (one 3-D box per operand, 128-byte swizzle, out-of-range rows read as
+//     zeros) and leave by TMA stores from the same ring: dy is formed IN PLACE over the y slab, dx in a small
+//     side buffer -- no per-thread global load or store in the loop;
+//   * fragments come from ldmatrix (x4) and go back with stmatrix (x4); the plan's A fragments for the dy
+//     product and the diag(ay) fragments live in registers for the whole item;
+//   * the plan W (fp32, written by the solver) of the NEXT item is prefetched by one bulk copy while the current
+//     item runs, then converted to bf16 (sign folded in) once per item.
+// Phases per slab: dx units (all warps read every y row) | barrier | dy tiles in place | barrier | stores.
+#include <algorithm>
+
+#include "ce_common.cuh"
+#include "ot_fused.cuh"
+
+namespace ce {
+
+int make_tmap3d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch,
+                     uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_inner, uint32_t box_rows);
+
+namespace {
+
+constexpr int kSlabCols = 64;      // bf16 columns per slab = one 128-byte swizzle row
+constexpr int kRowB = 128;         // bytes of one staged row
+constexpr int kRing = 3;
+
+struct WideGradParams {
+  int B, M, N, D;
+  int tiles_per_cta;   // 16-row tiles of image nodes per row split
+  int nsplit;          // row splits per sample (dx partials meet in dx_acc when > 1)
+  int dsplit;          // column ranges per sample
+  int nslab;           // D / 64
+  int ybox, nybox;     // rows per y TMA box, boxes per stage
+  const float* W;      // [B, N, MP] fp32 (scaled plan, model_ot.py:83 backward)
+  const float* ax;     // [B, MP]
+  const float* ay;     // [B, Nld]
+  int Nld;
+  float* dx_acc;       // [B, M, D] fp32 when nsplit > 1
+};
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(dst),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void stsm_x4(uint32_t addr, const uint32_t* r) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// byte offset of 16-byte chunk `chunk` of row `row` inside a 128-byte-swizzled tile whose base is 1024-byte aligned
+__device__ __forceinline__ uint32_t swz(int row, int chunk) {
+  return (uint32_t)(row * kRowB + ((chunk ^ (row & 7)) << 4));
+}
+
+struct WideLayout {
+  uint32_t stage_bytes, ring, dxout, wf, ayf, axf, axs, wb, bars, total;
+};
+__host__ __device__ inline WideLayout wide_layout(int MP, int rows) {
+  WideLayout L;
+  L.stage_bytes = (uint32_t)(MP + rows) * kRowB;
+  uint32_t off = 0;
+  L.ring = off; off += kRing * L.stage_bytes;
+  L.dxout = off; off += 2u * MP * kRowB;
+  L.wf = off; off += (uint32_t)rows * MP * 4;
+  L.ayf = off; off += (uint32_t)rows * 4 + 64;
+  L.axf = off; off += (uint32_t)MP * 4;
+  L.axs = off; off += (uint32_t)MP * 4;
+  L.wb = off; off += (uint32_t)rows * (MP + 8) * 2;
+  L.bars = off; off += 64;
+  L.total = off;
+  return L;
+}
+
+template <int MP, int TPW>
+__global__ void __launch_bounds__(512, 1)
+ot_wide_grad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+                    const __grid_constant__ CUtensorMap tmdx, const __grid_constant__ CUtensorMap tmdy,
+                    const WideGradParams a) {
+  constexpr int LDWB = MP + 8;          // bf16 plan row stride (elements): conflict-free ldmatrix rows
+  constexpr int KS = MP / 16;           // k-steps of the dy product
+  constexpr int NOUT = (MP / 16) * 8;   // dx output units (16 text rows x 8 columns) per slab
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
+  const int rows = a.tiles_per_cta * 16;
+  const WideLayout L = wide_layout(MP, rows);
+  float* Wf = reinterpret_cast<float*>(gbase + L.wf);
+  float* ayf = reinterpret_cast<float*>(gbase + L.ayf);
+  float* axf = reinterpret_cast<float*>(gbase + L.axf);
+  float* axs = reinterpret_cast<float*>(gbase + L.axs);
+  __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(gbase + L.wb);
+  uint64_t* full = reinterpret_cast<uint64_t*>(gbase + L.bars);   // [kRing]
+  uint64_t* wbar = full + kRing;
+  const uint32_t wb_u32 = sbase + L.wb;
+
+  const int tid = threadIdx.x, NT = blockDim.x, w = tid >> 5, nw = NT >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int per_sample = a.nsplit * a.dsplit;
+  const int items = a.B * per_sample;
+  const int ntiles = (a.N + 15) / 16;
+
+  auto geom = [&](int it, int& b, int& ns, int& c0, int& c1) {
+    b = it / per_sample;
+    const int rem = it - b * per_sample;
+    ns = rem / a.dsplit;
+    const int dh = rem - ns * a.dsplit;
+    c0 = dh * a.nslab / a.dsplit;
+    c1 = (dh + 1) * a.nslab / a.dsplit;
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) mbar_init(&full[s], 1);
+    mbar_init(wbar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // ---- producer state (thread 0 only): the slab after the last one issued ----------------------------
+  int l_it = blockIdx.x, l_b = 0, l_ns = 0, l_c = 0, l_c1 = 0;
+  if (l_it < items) geom(l_it, l_b, l_ns, l_c, l_c1);
+  auto issue_slab = [&](uint32_t q) {   // thread 0
+    if (l_it >= items) return;
+    const uint32_t s = q % kRing;
+    const uint32_t st = sbase + L.ring + s * L.stage_bytes;
+    mbar_expect_tx(&full[s], L.stage_bytes);
+    tma_load_3d_u32(st, &tmx, &full[s], l_c * kSlabCols, 0, l_b);
+    for (int k = 0; k < a.nybox; ++k)
+      tma_load_3d_u32(st + (uint32_t)(MP + k * a.ybox) * kRowB, &tmy, &full[s], l_c * kSlabCols,
+                      l_ns * rows + k * a.ybox, l_b);
+    if (++l_c == l_c1) {
+      l_it += gridDim.x;
+      if (l_it < items) geom(l_it, l_b, l_ns, l_c, l_c1);
+    }
+  };
+  auto issue_plan = [&](int it) {       // thread 0: W, ax, ay of item `it` into the fp32 staging buffers
+    int b, ns, c0, c1;
+    geom(it, b, ns, c0, c1);
+    const int row0 = ns * rows;
+    const int rv = min(rows, a.N - row0);
+    const uint32_t wbytes = (uint32_t)rv * MP * 4, abytes = (uint32_t)min(rows, a.Nld - row0) * 4;
+    mbar_expect_tx(wbar, wbytes + abytes + MP * 4);
+    bulk_load(Wf, a.W + ((int64_t)b * a.N + row0) * MP, wbytes, wbar);
+    bulk_load(ayf, a.ay + (int64_t)b * a.Nld + row0, abytes, wbar);
+    bulk_load(axf, a.ax + (int64_t)b * MP, MP * 4, wbar);
+  };
+  if (tid == 0 && blockIdx.x < items) {
+    issue_plan(blockIdx.x);
+    issue_slab(0);
+    issue_slab(1);
+  }
+
+  uint32_t q = 0;        // slabs consumed so far (ring position)
+  int item_k = 0;
+  for (int it = blockIdx.x; it < items; it += gridDim.x, ++item_k) {
+    int b, ns, c0, c1;
+    geom(it, b, ns, c0, c1);
+    const int row0 = ns * rows;
+    const int my_tiles = min(a.tiles_per_cta, ntiles - ns * a.tiles_per_cta);
+    const int rows_valid = min(rows, a.N - row0);
+
+    // ---- item start: plan -> bf16 (sign folded in), ax copy, fragments --------------------------------
+    mbar_wait(wbar, item_k & 1);
+    for (int idx = tid; idx < rows * (MP / 4); idx += NT) {
+      const int r = idx / (MP / 4), cq = (idx - r * (MP / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows_valid) v = *reinterpret_cast<const float4*>(Wf + r * MP + cq);
+      *reinterpret_cast<uint2*>(Wb + r * LDWB + cq) = make_uint2(pack2(-v.x, -v.y), pack2(-v.z, -v.w));
+    }
+    if (tid < MP) axs[tid] = axf[tid];
+    uint32_t dgh[TPW][2], dgl[TPW][2];   // diag(ay) A fragments: registers 0 and 3 (1, 2 are zero)
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+      const int r = (w + i * nw) * 16 + g;
+      const float ay0 = r < rows_valid ? ayf[r] : 0.f, ay1 = r + 8 < rows_valid ? ayf[r + 8] : 0.f;
+      const float h0 = bf16_round(ay0), h1 = bf16_round(ay1);
+      const bool e0 = (2 * t == g), e1 = (2 * t + 1 == g);
+      dgh[i][0] = pack2(e0 ? h0 : 0.f, e1 ? h0 : 0.f);
+      dgh[i][1] = pack2(e0 ? h1 : 0.f, e1 ? h1 : 0.f);
+      dgl[i][0] = pack2(e0 ? ay0 - h0 : 0.f, e1 ? ay0 - h0 : 0.f);
+      dgl[i][1] = pack2(e0 ? ay1 - h1 : 0.f, e1 ? ay1 - h1 : 0.f);
+    }
+    __syncthreads();
+    if (tid == 0 && it + (int)gridDim.x < items) issue_plan(it + gridDim.x);
+    uint32_t aw[TPW][KS][4];             // A fragments of (-W^t): rows = image nodes of the tile, k = text nodes
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+      const int tile = min(w + i * nw, a.tiles_per_cta - 1);
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        ldsm_x4(aw[i][ks], wb_u32 + (uint32_t)(((tile * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDWB + ks * 16 +
+                                                 (lane >> 4) * 8) * 2));
+    }
+
+    for (int c = c0; c < c1; ++c, ++q) {
+      const uint32_t s = q % kRing;
+      const uint32_t st = sbase + L.ring + s * L.stage_bytes;       // x rows, then y rows
+      const uint32_t sy = st + MP * kRowB;
+      const uint32_t dxo = sbase + L.dxout + (q & 1) * (MP * kRowB);
+      mbar_wait(&full[s], (q / kRing) & 1);
+
+      // ---- phase A: dx units (16 text rows x 8 columns), K = this CTA's image rows -------------------
+      for (int u = w; u < NOUT; u += nw) {
+        const int mi = u >> 3, j = u & 7;
+        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+        // A = W[m][n] out of Wb[n][m]: four transposed 8x8 blocks (m lo/hi x k lo/hi)
+        const int blk = lane >> 3, br = lane & 7;
+        uint32_t wa = wb_u32 + (uint32_t)(((br + (blk >> 1) * 8) * LDWB + 16 * mi + (blk & 1) * 8) * 2);
+        int ks = 0;
+        for (; ks + 1 < my_tiles; ks += 2) {
+          uint32_t a0[4], a1[4], bq[4];
+          ldsm_x4_t(a0, wa);
+          ldsm_x4_t(a1, wa + 16 * LDWB * 2);
+          ldsm_x4_t(bq, sy + swz(ks * 16 + lane, j));   // lanes 0-15: k-step ks, lanes 16-31: k-step ks + 1
+          mma16816(acc0, a0, bq[0], bq[1]);
+          mma16816(acc1, a1, bq[2], bq[3]);
+          wa += 32 * LDWB * 2;
+        }
+        if (ks < my_tiles) {
+          uint32_t a0[4], bq[2];
+          ldsm_x4_t(a0, wa);
+          ldsm_x2_t(bq, sy + swz(ks * 16 + (lane & 15), j));
+          mma16816(acc0, a0, bq[0], bq[1]);
+        }
+        const int m = 16 * mi + g;
+        if (a.nsplit == 1) {
+          const uint32_t o0 = swz(m, j) + 4 * t, o1 = swz(m + 8, j) + 4 * t;
+          const uint32_t u0 = lds32(st + o0), u1 = lds32(st + o1);
+          const float ax0 = axs[m], ax1 = axs[m + 8];
+          sts32(dxo + o0, pack2(fmaf(ax0, bf_lo(u0), acc0[0] + acc1[0]), fmaf(ax0, bf_hi(u0), acc0[1] + acc1[1])));
+          sts32(dxo + o1, pack2(fmaf(ax1, bf_lo(u1), acc0[2] + acc1[2]), fmaf(ax1, bf_hi(u1), acc0[3] + acc1[3])));
+        } else {
+          float* dacc = a.dx_acc + ((int64_t)b * a.M) * a.D + c * kSlabCols + 8 * j + 2 * t;
+          if (m < a.M) {
+            atomicAdd(dacc + (int64_t)m * a.D, acc0[0] + acc1[0]);
+            atomicAdd(dacc + (int64_t)m * a.D + 1, acc0[1] + acc1[1]);
+          }
+          if (m + 8 < a.M) {
+            atomicAdd(dacc + (int64_t)(m + 8) * a.D, acc0[2] + acc1[2]);
+            atomicAdd(dacc + (int64_t)(m + 8) * a.D + 1, acc0[3] + acc1[3]);
+          }
+        }
+      }
+      if (tid == 0) tma_store_wait_read();   // the previous slab's stores have left shared memory
+      __syncthreads();                       // every read of the y slab is done; stage (q + 2) % kRing is free
+      if (tid == 0) issue_slab(q + 2);
+
+      // ---- phase B: dy tiles in place: (-W^t) x + diag(ay) y -------------------------------------------
+#pragma unroll
+      for (int i = 0; i < TPW; ++i) {
+        const int tile = w + i * nw;
+        if (tile < my_tiles) {
+          float acc[8][4];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) acc[jj][cc] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2) {
+              uint32_t bq[4];
+              ldsm_x4_t(bq, st + swz(ks * 16 + (lane & 15), 2 * j2 + (lane >> 4)));
+              mma16816(acc[2 * j2], aw[i][ks], bq[0], bq[1]);
+              mma16816(acc[2 * j2 + 1], aw[i][ks], bq[2], bq[3]);
+            }
+          }
+          const uint32_t dh[4] = {dgh[i][0], 0u, 0u, dgh[i][1]}, dl[4] = {dgl[i][0], 0u, 0u, dgl[i][1]};
+#pragma unroll
+          for (int j2 = 0; j2 < 4; ++j2) {
+            uint32_t bq[4];
+            ldsm_x4_t(bq, sy + swz(tile * 16 + (lane & 15), 2 * j2 + (lane >> 4)));
+            mma16816(acc[2 * j2], dh, bq[0], bq[1]);
+            mma16816(acc[2 * j2], dl, bq[0], bq[1]);
+            mma16816(acc[2 * j2 + 1], dh, bq[2], bq[3]);
+            mma16816(acc[2 * j2 + 1], dl, bq[2], bq[3]);
+          }
+          const int q4 = lane >> 3;
+#pragma unroll
+          for (int j2 = 0; j2 < 4; ++j2) {
+            const uint32_t r4[4] = {pack2(acc[2 * j2][0], acc[2 * j2][1]), pack2(acc[2 * j2][2], acc[2 * j2][3]),
+                                    pack2(acc[2 * j2 + 1][0], acc[2 * j2 + 1][1]),
+                                    pack2(acc[2 * j2 + 1][2], acc[2 * j2 + 1][3])};
+            stsm_x4(sy + swz(tile * 16 + (lane & 7) + (q4 & 1) * 8, 2 * j2 + (q4 >> 1)), r4);
+          }
+        }
+      }
+      fence_proxy_async();                   // generic writes (dy in place, dx side buffer) -> TMA stores
+      __syncthreads();
+      if (tid == 0) {
+        if (a.nsplit == 1) tma_store_3d(&tmdx, dxo, c * kSlabCols, 0, b);
+        for (int k = 0; k < a.nybox; ++k)
+          if (k * a.ybox < rows_valid)
+            tma_store_3d(&tmdy, sy + (uint32_t)(k * a.ybox) * kRowB, c * kSlabCols, row0 + k * a.ybox, b);
+        tma_store_commit();
+      }
+    }
+  }
+  if (tid == 0) tma_store_wait_all();
+}
+
+struct WidePlan {
+  int MP, tiles_per_cta, nsplit, dsplit, ybox, nybox, tpw, nwarps, grid;
+  size_t smem;
+};
+
+bool plan_wide(int B, int M, int N, int D, WidePlan* p) {
+  if (M < 1 || M > 64 || N < 1 || N > 1024 || D < kSlabCols || D % kSlabCols != 0) return false;
+  p->MP = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
+  const int ntiles = (N + 15) / 16;
+  int cap = std::min(ntiles, 32);
+  while (cap > 1 && wide_layout(p->MP, cap * 16).total + 1024 > 200 * 1024) --cap;
+  p->nsplit = (ntiles + cap - 1) / cap;
+  p->tiles_per_cta = (ntiles + p->nsplit - 1) / p->nsplit;
+  const int rows = p->tiles_per_cta * 16;
+  p->smem = wide_layout(p->MP, rows).total + 1024;
+  // TMA boxes hold at most 256 rows; two boxes of rows / 2 (a multiple of 8 rows: the second box stays
+  // 1024-byte aligned) otherwise
+  if (rows <= 256) { p->ybox = rows; p->nybox = 1; }
+  else { p->ybox = rows / 2; p->nybox = 2; }
+  p->tpw = p->tiles_per_cta > 16 ? 2 : 1;
+  p->nwarps = std::max(4, (p->tiles_per_cta + p->tpw - 1) / p->tpw);
+  int ctas_per_sm = std::max(1, std::min((int)((227 * 1024) / p->smem), 2048 / (p->nwarps * 32)));
+  ctas_per_sm = std::min(ctas_per_sm, 4);
+  const int slots = num_sms() * ctas_per_sm;
+  // column ranges: fine enough that the item count divides evenly over the persistent CTAs, at least 3 slabs each
+  const int nslab = D / kSlabCols;
+  int best = 1;
+  double best_waste = 1e9;
+  for (int ds = 1; ds <= nslab; ++ds) {
+    if (nslab % ds != 0 || (nslab / ds < 3 && ds > 1)) continue;
+    const int64_t items = (int64_t)B * p->nsplit * ds;
+    const int64_t per = (items + slots - 1) / slots;
+    const double waste = (double)(per * slots) / (double)items;
+    if (waste < best_waste - 0.02) { best_waste = waste; best = ds; }
+  }
+  p->dsplit = best;
+  p->grid = (int)std::min<int64_t>((int64_t)B * p->nsplit * p->dsplit, slots);
+  return true;
+}
+
+template <int MP, int TPW>
+int launch_cfg(const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tdx, const CUtensorMap& tdy,
+               const WideGradParams& a, const WidePlan& p, cudaStream_t st) {
+  auto kern = ot_wide_grad_kernel<MP, TPW>;
+  CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  kern<<<p.grid, p.nwarps * 32, p.smem, st>>>(tx, ty, tdx, tdy, a);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}
+
+}  // namespace
+
+bool ot_wide_supported(int M, int N, int D, int dtype) {
+  static const bool on = [] { const char* e = getenv("CE_OT_WIDE"); return e == nullptr || atoi(e) != 0; }();
+  WidePlan p;
+  return on && dtype == CE_BF16 && plan_wide(1, M, N, D, &p);
+}
+int ot_wide_nsplit(int M, int N, int D) {
+  WidePlan p;
+  return plan_wide(1, M, N, D, &p) ? p.nsplit : 1;
+}
+
+int launch_ot_wide_grad(const OtWideGradArgs& g, cudaStream_t st) {
+  WidePlan p;
+  if (!plan_wide(g.B, g.M, g.N, g.D, &p)) return fail(CE_ERR_SHAPE, "OT wide gradient: unsupported shape");
+  CUtensorMap tx, ty, tdx, tdy;
+  const int rows = p.tiles_per_cta * 16;
+  (void)rows;
+  CE_TRY(make_tmap3d_bf16(&tx, g.txt, g.D, g.M, g.B, g.D, g.txt_bs, kSlabCols, p.MP));
+  CE_TRY(make_tmap3d_bf16(&ty, g.img, g.D, g.N, g.B, g.D, g.img_bs, kSlabCols, p.ybox));
+  CE_TRY(make_tmap3d_bf16(&tdx, g.dtxt, g.D, g.M, g.B, g.D, g.txt_bs, kSlabCols, p.MP));
+  CE_TRY(make_tmap3d_bf16(&tdy, g.dimg, g.D, g.N, g.B, g.D, g.img_bs, kSlabCols, p.ybox));
+  WideGradParams a{};
+  a.B = g.B; a.M = g.M; a.N = g.N; a.D = g.D;
+  a.tiles_per_cta = p.tiles_per_cta; a.nsplit = p.nsplit; a.dsplit = p.dsplit; a.nslab = g.D / kSlabCols;
+  a.ybox = p.ybox; a.nybox = p.nybox;
+  a.W = g.W; a.ax = g.ax; a.ay = g.ay; a.Nld = g.Nld; a.dx_acc = g.dx_acc;
+  if (p.nsplit > 1 && g.dx_acc == nullptr) return fail(CE_ERR_ARG, "OT wide gradient: dx accumulator missing");
+  switch (p.MP * 10 + p.tpw) {
+    case 161: return launch_cfg<16, 1>(tx, ty, tdx, tdy, a, p, st);
+    case 162: return launch_cfg<16, 2>(tx, ty, tdx, tdy, a, p, st);
+    case 321: return launch_cfg<32, 1>(tx, ty, tdx, tdy, a, p, st);
+    case 322: return launch_cfg<32, 2>(tx, ty, tdx, tdy, a, p, st);
+    case 641: return launch_cfg<64, 1>(tx, ty, tdx, tdy, a, p, st);
+    default: return launch_cfg<64, 2>(tx, ty, tdx, tdy, a, p, st);
+  }
+}
+
+}  // namespace ce
