@@ -29,7 +29,7 @@ namespace {
 
 constexpr int kSlabCols = 64;      // bf16 columns per slab = one 128-byte swizzle row
 constexpr int kRowB = 128;         // bytes of one staged row
-constexpr int kRing = 3;
+constexpr int kMaxRing = 8;      // slab ring depth: as many stages as shared memory holds (plan_wide)
 
 struct WideGradParams {
   int B, M, N, D;
@@ -38,6 +38,8 @@ struct WideGradParams {
   int dsplit;          // column ranges per sample
   int nslab;           // D / 64
   int ybox, nybox;     // rows per y TMA box, boxes per stage
+  int ring;            // stages of the slab ring
+  int dbg;             // CE_OT_WIDE_DBG (timing aid): 1 = no dx phase, 2 = no dy phase, 3 = copy only (garbage out)
   const float* W;      // [B, N, MP] fp32 (scaled plan, model_ot.py:83 backward)
   const float* ax;     // [B, MP]
   const float* ay;     // [B, Nld]
@@ -112,24 +114,27 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) {
 struct WideLayout {
   uint32_t stage_bytes, ring, dxout, wf, ayf, axf, axs, wb, bars, total;
 };
-__host__ __device__ inline WideLayout wide_layout(int MP, int rows) {
+__host__ __device__ inline WideLayout wide_layout(int MP, int rows, int kRing) {
   WideLayout L;
   L.stage_bytes = (uint32_t)(MP + rows) * kRowB;
   uint32_t off = 0;
   L.ring = off; off += kRing * L.stage_bytes;
-  L.dxout = off; off += 2u * MP * kRowB;
+  L.dxout = off; off += 3u * MP * kRowB;
   L.wf = off; off += (uint32_t)rows * MP * 4;
   L.ayf = off; off += (uint32_t)rows * 4 + 64;
   L.axf = off; off += (uint32_t)MP * 4;
   L.axs = off; off += (uint32_t)MP * 4;
   L.wb = off; off += (uint32_t)rows * (MP + 8) * 2;
-  L.bars = off; off += 64;
+  L.bars = off; off += 8 * (kMaxRing + 1);
   L.total = off;
   return L;
 }
 
-template <int MP, int TPW>
-__global__ void __launch_bounds__(512, 1)
+// KT > 0: the dx product keeps the plan in REGISTERS (K-steps 0..KT-1 of 16 text rows x 16 image rows per warp,
+// warp = (16 text rows, 16 columns)): shared-memory wavefronts per slab 1632 -> 544 (the first version was bound
+// by the shared-memory pipe: 6 wavefronts per MMA).  Needs MP <= 32 and at most KT row tiles per CTA.
+template <int MP, int TPW, int KT>
+__global__ void __launch_bounds__(KT > 0 ? 320 : (TPW == 1 ? 576 : 512), 1)
 ot_wide_grad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
                     const __grid_constant__ CUtensorMap tmdx, const __grid_constant__ CUtensorMap tmdy,
                     const WideGradParams a) {
@@ -140,14 +145,15 @@ ot_wide_grad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
   const int rows = a.tiles_per_cta * 16;
-  const WideLayout L = wide_layout(MP, rows);
+  const int kRing = a.ring;
+  const WideLayout L = wide_layout(MP, rows, kRing);
   float* Wf = reinterpret_cast<float*>(gbase + L.wf);
   float* ayf = reinterpret_cast<float*>(gbase + L.ayf);
   float* axf = reinterpret_cast<float*>(gbase + L.axf);
   float* axs = reinterpret_cast<float*>(gbase + L.axs);
   __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(gbase + L.wb);
   uint64_t* full = reinterpret_cast<uint64_t*>(gbase + L.bars);   // [kRing]
-  uint64_t* wbar = full + kRing;
+  uint64_t* wbar = full + kMaxRing;
   const uint32_t wb_u32 = sbase + L.wb;
 
   const int tid = threadIdx.x, NT = blockDim.x, w = tid >> 5, nw = NT >> 5, lane = tid & 31;
@@ -165,8 +171,19 @@ ot_wide_grad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
     c1 = (dh + 1) * a.nslab / a.dsplit;
   };
 
-  if (tid == 0) {
+  // Per-lane fragment offsets inside a swizzled tile, fixed for the whole kernel (row blocks are multiples of 8 rows,
+  // so a tile / k-step only adds a multiple of 2048 bytes).  Pinned to registers: recomputing the XOR swizzle at
+  // every ldmatrix was a third of the dy phase's instructions.
+  const int q4 = lane >> 3;
+  uint32_t lo4[4], so4[4];
 #pragma unroll
+  for (int j2 = 0; j2 < 4; ++j2) {
+    lo4[j2] = swz(lane & 15, 2 * j2 + (lane >> 4));                      // B fragments: 16 rows x 2 chunks
+    so4[j2] = swz((lane & 7) + (q4 & 1) * 8, 2 * j2 + (q4 >> 1));        // stmatrix of an accumulator pair
+    asm volatile("" : "+r"(lo4[j2]), "+r"(so4[j2]));
+  }
+
+  if (tid == 0) {
     for (int s = 0; s < kRing; ++s) mbar_init(&full[s], 1);
     mbar_init(wbar, 1);
     mbar_fence_init();
@@ -203,8 +220,7 @@ ot_wide_grad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
   };
   if (tid == 0 && blockIdx.x < items) {
     issue_plan(blockIdx.x);
-    issue_slab(0);
-    issue_slab(1);
+    for (int s = 0; s + 2 < kRing; ++s) issue_slab(s);
   }
 
   uint32_t q = 0;        // slabs consumed so far (ring position)
@@ -239,24 +255,87 @@ ot_wide_grad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
     }
     __syncthreads();
     if (tid == 0 && it + (int)gridDim.x < items) issue_plan(it + gridDim.x);
-    uint32_t aw[TPW][KS][4];             // A fragments of (-W^t): rows = image nodes of the tile, k = text nodes
+    // A fragments of (-W^t) for the dy product (rows = image nodes of a tile, k = text nodes): per-lane address of
+    // tile 0; the slab loop re-reads them (4 ldmatrix per tile) instead of holding 16 registers across the item
+    const uint32_t awo = wb_u32 + (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * LDWB + (lane >> 4) * 8) * 2);
+    // register-resident plan for the dx product: B fragments (k = image rows, n = 16 text rows of this warp)
+    constexpr int KTR = KT > 0 ? KT : 1;
+    uint32_t wreg[KTR][4];
+    float axr[2][2];
+    const int mg = w >> 2, cb = w & 3;    // text-row group (16 rows), column block (16 columns) of this warp
+    const bool dx_warp = KT > 0 && w < (MP / 16) * 4;
+    if constexpr (KT > 0) {
+      if (dx_warp) {
 #pragma unroll
-    for (int i = 0; i < TPW; ++i) {
-      const int tile = min(w + i * nw, a.tiles_per_cta - 1);
+        for (int ks = 0; ks < KT; ++ks) {
+          if (ks < my_tiles)
+            ldsm_x4_t(wreg[ks], wb_u32 + (uint32_t)(((ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDWB + mg * 16 +
+                                                      (lane >> 4) * 8) * 2));
+          else wreg[ks][0] = wreg[ks][1] = wreg[ks][2] = wreg[ks][3] = 0u;
+        }
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
-        ldsm_x4(aw[i][ks], wb_u32 + (uint32_t)(((tile * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDWB + ks * 16 +
-                                                 (lane >> 4) * 8) * 2));
+        for (int nt = 0; nt < 2; ++nt) {
+          axr[nt][0] = axs[mg * 16 + nt * 8 + 2 * t];
+          axr[nt][1] = axs[mg * 16 + nt * 8 + 2 * t + 1];
+        }
+      }
     }
 
     for (int c = c0; c < c1; ++c, ++q) {
       const uint32_t s = q % kRing;
       const uint32_t st = sbase + L.ring + s * L.stage_bytes;       // x rows, then y rows
       const uint32_t sy = st + MP * kRowB;
-      const uint32_t dxo = sbase + L.dxout + (q & 1) * (MP * kRowB);
+      const uint32_t dxo = sbase + L.dxout + (q % 3) * (MP * kRowB);
       mbar_wait(&full[s], (q / kRing) & 1);
 
-      // ---- phase A: dx units (16 text rows x 8 columns), K = this CTA's image rows -------------------
+      // ---- phase A: dx, K = this CTA's image rows ------------------------------------------------------
+      if constexpr (KT > 0) {
+        if (dx_warp && !(a.dbg & 1)) {
+          // D[d][m] = sum_n y[n][d] (-W)[m][n]: A = y^t out of the slab (transposed ldmatrix), B = the plan registers
+          float acc[2][2][4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) acc[e][nt][cc] = 0.f;
+          uint32_t ao = sy + swz((lane & 7) + (q4 >> 1) * 8, 2 * cb + (q4 & 1));
+          // K-steps past this item's tiles multiply zero plan registers; their addresses stay inside the stage
+          const uint32_t kmax = (uint32_t)(a.tiles_per_cta - 1) * 2048u;
+#pragma unroll
+          for (int ks = 0; ks < KT; ++ks) {
+            uint32_t aq[4];
+            ldsm_x4_t(aq, ao + min((uint32_t)ks * 2048u, kmax));
+            mma16816(acc[ks & 1][0], aq, wreg[ks][0], wreg[ks][1]);
+            mma16816(acc[ks & 1][1], aq, wreg[ks][2], wreg[ks][3]);
+          }
+          // fragment (d = g / g + 8, m = 2t, 2t + 1) of text-row block nt; x comes in and dx goes out transposed
+          const uint32_t xo = swz(mg * 16 + (q4 >> 1) * 8 + (lane & 7), 2 * cb + (q4 & 1));
+          if (a.nsplit == 1) {
+            uint32_t xq[4], oq[4];
+            ldsm_x4_t(xq, st + xo);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int db = 0; db < 2; ++db) {
+                const uint32_t xv = xq[nt * 2 + db];
+                oq[nt * 2 + db] = pack2(fmaf(axr[nt][0], bf_lo(xv), acc[0][nt][2 * db] + acc[1][nt][2 * db]),
+                                        fmaf(axr[nt][1], bf_hi(xv), acc[0][nt][2 * db + 1] + acc[1][nt][2 * db + 1]));
+              }
+            asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(dxo + xo),
+                         "r"(oq[0]), "r"(oq[1]), "r"(oq[2]), "r"(oq[3])
+                         : "memory");
+          } else {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                const int m = mg * 16 + nt * 8 + 2 * t + (cc & 1), d = c * kSlabCols + cb * 16 + g + (cc >> 1) * 8;
+                if (m < a.M) atomicAdd(a.dx_acc + ((int64_t)b * a.M + m) * a.D + d, acc[0][nt][cc] + acc[1][nt][cc]);
+              }
+          }
+        }
+      } else {
       for (int u = w; u < NOUT; u += nw) {
         const int mi = u >> 3, j = u & 7;
         float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -298,15 +377,18 @@ ot_wide_grad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
           }
         }
       }
-      if (tid == 0) tma_store_wait_read();   // the previous slab's stores have left shared memory
-      __syncthreads();                       // every read of the y slab is done; stage (q + 2) % kRing is free
-      if (tid == 0) issue_slab(q + 2);
+      }
+      // the stores of slab q - 2 have left shared memory (those of slab q - 1 may still be draining: waiting for
+      // them here tied every slab to the drain time of the previous one)
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();                       // every read of the y slab is done; stage (q - 2) % ring is free
+      if (tid == 0) issue_slab(q + kRing - 2);
 
       // ---- phase B: dy tiles in place: (-W^t) x + diag(ay) y -------------------------------------------
 #pragma unroll
       for (int i = 0; i < TPW; ++i) {
         const int tile = w + i * nw;
-        if (tile < my_tiles) {
+        if (tile < my_tiles && !(a.dbg & 2)) {
           float acc[8][4];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj)
@@ -314,31 +396,32 @@ ot_wide_grad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
             for (int cc = 0; cc < 4; ++cc) acc[jj][cc] = 0.f;
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) {
+            uint32_t aw[4];
+            ldsm_x4(aw, awo + (uint32_t)((tile * 16 * LDWB + ks * 16) * 2));
 #pragma unroll
             for (int j2 = 0; j2 < 4; ++j2) {
               uint32_t bq[4];
-              ldsm_x4_t(bq, st + swz(ks * 16 + (lane & 15), 2 * j2 + (lane >> 4)));
-              mma16816(acc[2 * j2], aw[i][ks], bq[0], bq[1]);
-              mma16816(acc[2 * j2 + 1], aw[i][ks], bq[2], bq[3]);
+              ldsm_x4_t(bq, st + lo4[j2] + ks * 2048);
+              mma16816(acc[2 * j2], aw, bq[0], bq[1]);
+              mma16816(acc[2 * j2 + 1], aw, bq[2], bq[3]);
             }
           }
           const uint32_t dh[4] = {dgh[i][0], 0u, 0u, dgh[i][1]}, dl[4] = {dgl[i][0], 0u, 0u, dgl[i][1]};
 #pragma unroll
           for (int j2 = 0; j2 < 4; ++j2) {
             uint32_t bq[4];
-            ldsm_x4_t(bq, sy + swz(tile * 16 + (lane & 15), 2 * j2 + (lane >> 4)));
+            ldsm_x4_t(bq, sy + lo4[j2] + tile * 2048);
             mma16816(acc[2 * j2], dh, bq[0], bq[1]);
             mma16816(acc[2 * j2], dl, bq[0], bq[1]);
             mma16816(acc[2 * j2 + 1], dh, bq[2], bq[3]);
             mma16816(acc[2 * j2 + 1], dl, bq[2], bq[3]);
           }
-          const int q4 = lane >> 3;
 #pragma unroll
           for (int j2 = 0; j2 < 4; ++j2) {
             const uint32_t r4[4] = {pack2(acc[2 * j2][0], acc[2 * j2][1]), pack2(acc[2 * j2][2], acc[2 * j2][3]),
                                     pack2(acc[2 * j2 + 1][0], acc[2 * j2 + 1][1]),
                                     pack2(acc[2 * j2 + 1][2], acc[2 * j2 + 1][3])};
-            stsm_x4(sy + swz(tile * 16 + (lane & 7) + (q4 & 1) * 8, 2 * j2 + (q4 >> 1)), r4);
+            stsm_x4(sy + so4[j2] + tile * 2048, r4);
           }
         }
       }
@@ -357,7 +440,7 @@ ot_wide_grad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
 }
 
 struct WidePlan {
-  int MP, tiles_per_cta, nsplit, dsplit, ybox, nybox, tpw, nwarps, grid;
+  int MP, tiles_per_cta, nsplit, dsplit, ybox, nybox, tpw, nwarps, grid, ring, kt;
   size_t smem;
 };
 
@@ -365,18 +448,39 @@ bool plan_wide(int B, int M, int N, int D, WidePlan* p) {
   if (M < 1 || M > 64 || N < 1 || N > 1024 || D < kSlabCols || D % kSlabCols != 0) return false;
   p->MP = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
   const int ntiles = (N + 15) / 16;
+  constexpr size_t kSmemMax = 226 * 1024;
   int cap = std::min(ntiles, 32);
-  while (cap > 1 && wide_layout(p->MP, cap * 16).total + 1024 > 200 * 1024) --cap;
+  while (cap > 1 && wide_layout(p->MP, cap * 16, 4).total + 1024 > kSmemMax) --cap;
   p->nsplit = (ntiles + cap - 1) / cap;
   p->tiles_per_cta = (ntiles + p->nsplit - 1) / p->nsplit;
   const int rows = p->tiles_per_cta * 16;
-  p->smem = wide_layout(p->MP, rows).total + 1024;
+  // ring depth: the loads in flight per SM hide the HBM latency (3 stages left ~1.5 slabs of lead: 3.8 TB/s at c4);
+  // small plans share the SM between several CTAs instead of growing one ring
+  p->ring = 4;   // the loop reloads the stage of slab q - 2: two slabs of lead need four stages
+  while (p->ring < 7 && wide_layout(p->MP, rows, p->ring + 1).total + 1024 <= (rows >= 128 ? kSmemMax : 72 * 1024)) ++p->ring;
+  {   // tuning aid: CE_OT_WIDE_RING forces the ring depth (when it fits)
+    static const int ring_env = [] { const char* e = getenv("CE_OT_WIDE_RING"); return e != nullptr ? atoi(e) : 0; }();
+    if (ring_env >= 3 && ring_env <= kMaxRing && wide_layout(p->MP, rows, ring_env).total + 1024 <= kSmemMax) p->ring = ring_env;
+  }
+  p->smem = wide_layout(p->MP, rows, p->ring).total + 1024;
   // TMA boxes hold at most 256 rows; two boxes of rows / 2 (a multiple of 8 rows: the second box stays
   // 1024-byte aligned) otherwise
   if (rows <= 256) { p->ybox = rows; p->nybox = 1; }
   else { p->ybox = rows / 2; p->nybox = 2; }
-  p->tpw = p->tiles_per_cta > 16 ? 2 : 1;
+  // one warp per 16-row tile up to 18 tiles (c4: 17 warps, every phase balanced; 9 warps with two tiles each left
+  // 2.25 warps per scheduler and 9 cycles between issues), two tiles per warp beyond
+  static const int tpw1_max = [] { const char* e = getenv("CE_OT_WIDE_TPW1"); return e != nullptr ? atoi(e) : 18; }();
+  p->tpw = p->tiles_per_cta > tpw1_max ? 2 : 1;
   p->nwarps = std::max(4, (p->tiles_per_cta + p->tpw - 1) / p->tpw);
+  // register-resident plan for the dx product (KT = 17 or 20 K-steps): 9..20 row tiles, MP <= 32; two tiles per warp, and at least
+  // the (MP / 16) x 4 warps of the dx phase
+  static const bool res_on = [] { const char* e = getenv("CE_OT_WIDE_RES"); return e == nullptr || atoi(e) != 0; }();
+  p->kt = 0;
+  if (res_on && p->MP <= 32 && p->tiles_per_cta >= 9 && p->tiles_per_cta <= 20) {
+    p->kt = p->tiles_per_cta <= 17 ? 17 : 20;
+    p->tpw = 2;
+    p->nwarps = std::max((p->tiles_per_cta + 1) / 2, (p->MP / 16) * 4);
+  }
   int ctas_per_sm = std::max(1, std::min((int)((227 * 1024) / p->smem), 2048 / (p->nwarps * 32)));
   ctas_per_sm = std::min(ctas_per_sm, 4);
   const int slots = num_sms() * ctas_per_sm;
@@ -396,10 +500,10 @@ bool plan_wide(int B, int M, int N, int D, WidePlan* p) {
   return true;
 }
 
-template <int MP, int TPW>
+template <int MP, int TPW, int KT = 0>
 int launch_cfg(const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tdx, const CUtensorMap& tdy,
                const WideGradParams& a, const WidePlan& p, cudaStream_t st) {
-  auto kern = ot_wide_grad_kernel<MP, TPW>;
+  auto kern = ot_wide_grad_kernel<MP, TPW, KT>;
   CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   kern<<<p.grid, p.nwarps * 32, p.smem, st>>>(tx, ty, tdx, tdy, a);
   CE_LAUNCH_CHECK();
@@ -431,9 +535,14 @@ int launch_ot_wide_grad(const OtWideGradArgs& g, cudaStream_t st) {
   WideGradParams a{};
   a.B = g.B; a.M = g.M; a.N = g.N; a.D = g.D;
   a.tiles_per_cta = p.tiles_per_cta; a.nsplit = p.nsplit; a.dsplit = p.dsplit; a.nslab = g.D / kSlabCols;
-  a.ybox = p.ybox; a.nybox = p.nybox;
+  a.ybox = p.ybox; a.nybox = p.nybox; a.ring = p.ring;
+  { static const int dbg = [] { const char* e = getenv("CE_OT_WIDE_DBG"); return e != nullptr ? atoi(e) : 0; }(); a.dbg = dbg; }
   a.W = g.W; a.ax = g.ax; a.ay = g.ay; a.Nld = g.Nld; a.dx_acc = g.dx_acc;
   if (p.nsplit > 1 && g.dx_acc == nullptr) return fail(CE_ERR_ARG, "OT wide gradient: dx accumulator missing");
+  if (p.kt == 17 && p.MP == 16) return launch_cfg<16, 2, 17>(tx, ty, tdx, tdy, a, p, st);
+  if (p.kt == 17 && p.MP == 32) return launch_cfg<32, 2, 17>(tx, ty, tdx, tdy, a, p, st);
+  if (p.kt == 20 && p.MP == 16) return launch_cfg<16, 2, 20>(tx, ty, tdx, tdy, a, p, st);
+  if (p.kt == 20 && p.MP == 32) return launch_cfg<32, 2, 20>(tx, ty, tdx, tdy, a, p, st);
   switch (p.MP * 10 + p.tpw) {
     case 161: return launch_cfg<16, 1>(tx, ty, tdx, tdy, a, p, st);
     case 162: return launch_cfg<16, 2>(tx, ty, tdx, tdy, a, p, st);
