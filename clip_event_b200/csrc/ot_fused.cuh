@@ -60,5 +60,15 @@ struct OtWideGradArgs {
 bool ot_wide_supported(int M, int N, int D, int dtype);
 int ot_wide_nsplit(int M, int N, int D);
 int launch_ot_wide_grad(const OtWideGradArgs& g, cudaStream_t st);
+// Cost contraction of the same family: S = y x^t (fp32 [B, N, MP]) and the rows' sums of squares.
+struct OtWideCostArgs {
+  const void* txt; const void* img;
+  int64_t txt_bs, img_bs;
+  int B, M, N, D;
+  float* S; float* nx2; float* ny2;
+  int Nld;
+};
+bool ot_wide_cost_supported(int M, int N, int D, int dtype);
+int launch_ot_wide_cost(const OtWideCostArgs& g, cudaStream_t st);
 
 }  // namespace ce

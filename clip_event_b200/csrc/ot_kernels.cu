@@ -1388,7 +1388,12 @@ extern "C" int ce_ot_fwd_bwd(const void* txt, int64_t txt_bstride, const void* i
   const int grad_nsplit = wide_grad ? ot_wide_nsplit(M, N, D) : p.nsplit;
   a.dx_acc = (p.nsplit > 1 || grad_nsplit > 1) ? cv.take<float>((size_t)B * M * D) : nullptr;
 
-  if (dtype == CE_F32) CE_TRY(dispatch_mp<CE_F32>(false, a, p, st));
+  if (ot_wide_cost_supported(M, N, D, dtype)) {   // bf16: TMA-fed persistent kernel (csrc/ot_wide.cu)
+    OtWideCostArgs wc{};
+    wc.txt = txt; wc.img = img; wc.txt_bs = txt_bstride; wc.img_bs = img_bstride;
+    wc.B = B; wc.M = M; wc.N = N; wc.D = D; wc.S = a.S; wc.nx2 = a.nx2; wc.ny2 = a.ny2; wc.Nld = Nld;
+    CE_TRY(launch_ot_wide_cost(wc, st));
+  } else if (dtype == CE_F32) CE_TRY(dispatch_mp<CE_F32>(false, a, p, st));
   else CE_TRY(dispatch_mp<CE_BF16>(false, a, p, st));
 
   IpotArgs ia{};

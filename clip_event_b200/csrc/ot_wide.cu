@@ -439,6 +439,187 @@ ot_wide_grad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
   if (tid == 0) tma_store_wait_all();
 }
 
+// ------------------------------------------------------------------------------------------
+// Cost contraction for the same plans: S[n][m] = <y_n, x_m> (fp32, [B, N, MP]) and the rows' sums of squares
+// (model_ot.py:8-18 before the normalisation, which the solver applies).  Reads x, y once.  Same TMA ring as
+// above, but nothing is stored from it, so there is no CTA-wide barrier at all: one extra warp produces (and takes
+// the text rows' sums of squares from each slab), the tile warps release a stage through an mbarrier.
+// ------------------------------------------------------------------------------------------
+struct WideCostParams {
+  int B, M, N, D;
+  int tiles_per_cta, nsplit, nslab, ybox, nybox, ring;
+  float* S;      // [B, N, MP]
+  float* nx2;    // [B, MP]
+  float* ny2;    // [B, Nld]
+  int Nld;
+};
+
+template <int MP, int TPW>
+__global__ void __launch_bounds__(TPW == 1 ? 576 : 352, 1)
+ot_wide_cost_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+                    const WideCostParams a) {
+  constexpr int NJ = MP / 8;            // 8-column blocks of text nodes
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
+  const int rows = a.tiles_per_cta * 16;
+  const uint32_t stage_bytes = (uint32_t)(MP + rows) * kRowB;
+  const int R = a.ring;
+  uint64_t* full = reinterpret_cast<uint64_t*>(gbase + (size_t)R * stage_bytes);
+  uint64_t* empty = full + kMaxRing;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int nw = (blockDim.x >> 5) - 1;          // tile warps; warp nw produces
+  const int items = a.B * a.nsplit;
+  const int ntiles = (a.N + 15) / 16;
+
+  if (tid == 0) {
+    for (int s = 0; s < R; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nw + 1); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (w == nw) {
+    // ---- producer + text-row norms ---------------------------------------------------------------------
+    int l_it = blockIdx.x, l_c = 0;
+    auto issue = [&](uint32_t p) {             // one lane
+      if (l_it >= items) return;
+      const uint32_t s = p % R, st = sbase + s * stage_bytes;
+      const int b = l_it / a.nsplit, ns = l_it - b * a.nsplit;
+      mbar_expect_tx(&full[s], stage_bytes);
+      tma_load_3d_u32(st, &tmx, &full[s], l_c * kSlabCols, 0, b);
+      for (int k = 0; k < a.nybox; ++k)
+        tma_load_3d_u32(st + (uint32_t)(MP + k * a.ybox) * kRowB, &tmy, &full[s], l_c * kSlabCols,
+                        ns * rows + k * a.ybox, b);
+      if (++l_c == a.nslab) { l_c = 0; l_it += gridDim.x; }
+    };
+    if (lane == 0)
+      for (int p = 0; p + 1 < R; ++p) issue(p);
+    uint32_t q = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int b = it / a.nsplit, ns = it - b * a.nsplit;
+      float ss[MP > 32 ? 2 : 1] = {};
+      for (int c = 0; c < a.nslab; ++c, ++q) {
+        if (lane == 0 && q > 0) {              // stage of slab q - 1: free once every warp has released it
+          const uint32_t pq = q - 1;
+          mbar_wait(&empty[pq % R], (pq / R) & 1);
+          issue(q + R - 1);
+        } else if (lane == 0) {
+          // first slab: nothing to release, the prologue filled R - 1 stages; stage R - 1 is free
+          issue(R - 1);
+        }
+        __syncwarp();
+        const uint32_t s = q % R, st = sbase + s * stage_bytes;
+        mbar_wait(&full[s], (q / R) & 1);
+#pragma unroll
+        for (int h = 0; h < (MP > 32 ? 2 : 1); ++h) {
+          const int m = lane + 32 * h;
+          if (m < MP) {
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              uint4 v;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                           : "r"(st + swz(m, ch)));
+              const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float lo = bf_lo(wv[e]), hi = bf_hi(wv[e]);
+                ss[h] = fmaf(lo, lo, ss[h]);
+                ss[h] = fmaf(hi, hi, ss[h]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+      if (ns == 0) {
+#pragma unroll
+        for (int h = 0; h < (MP > 32 ? 2 : 1); ++h)
+          if (lane + 32 * h < MP) a.nx2[(int64_t)b * MP + lane + 32 * h] = ss[h];
+      }
+    }
+    return;
+  }
+
+  // ---- tile warps ------------------------------------------------------------------------------------------
+  uint32_t ao[TPW];
+#pragma unroll
+  for (int i = 0; i < TPW; ++i) {
+    const int tile = min(w + i * nw, a.tiles_per_cta - 1);
+    // A fragment (16 image rows x 16 columns): row = lane & 7 (+8 for matrices 1, 3), chunk = 2 ks + (lane >> 4)
+    ao[i] = (uint32_t)(MP + tile * 16 + (lane & 7) + ((lane >> 3) & 1) * 8);
+  }
+  uint32_t q = 0;
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int b = it / a.nsplit, ns = it - b * a.nsplit;
+    const int row0 = ns * rows;
+    const int my_tiles = min(a.tiles_per_cta, ntiles - ns * a.tiles_per_cta);
+    const int rows_valid = min(rows, a.N - row0);
+    float acc[TPW][NJ][4], yd[TPW][2][4];
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) yd[i][0][cc] = yd[i][1][cc] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) acc[i][j][cc] = 0.f;
+    }
+    for (int c = 0; c < a.nslab; ++c, ++q) {
+      const uint32_t s = q % R, st = sbase + s * stage_bytes;
+      mbar_wait(&full[s], (q / R) & 1);
+      if (w < my_tiles) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          // B fragments: text rows m on the n axis, k = columns; one x4 covers two 8-row blocks
+          uint32_t bf[NJ / 2][4];
+#pragma unroll
+          for (int p2 = 0; p2 < NJ / 2; ++p2)
+            ldsm_x4(bf[p2], st + swz(p2 * 16 + (lane & 7) + (lane >> 4) * 8, 2 * ks + ((lane >> 3) & 1)));
+#pragma unroll
+          for (int i = 0; i < TPW; ++i) {
+            if (i == 0 || w + i * nw < my_tiles) {
+              uint32_t af[4];
+              ldsm_x4(af, st + swz((int)ao[i], 2 * ks + (lane >> 4)));
+              mma16816(yd[i][0], af, af[0], af[2]);      // rows x rows 0-7 of the same tile: diagonal = |y|^2
+              mma16816(yd[i][1], af, af[1], af[3]);
+#pragma unroll
+              for (int p2 = 0; p2 < NJ / 2; ++p2) {
+                mma16816(acc[i][2 * p2], af, bf[p2][0], bf[p2][1]);
+                mma16816(acc[i][2 * p2 + 1], af, bf[p2][2], bf[p2][3]);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    // ---- item end: S rows and |y|^2 of this warp's tiles ---------------------------------------------------
+    float* Sg = a.S + ((int64_t)b * a.N + row0) * MP;
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+      const int tile = w + i * nw;
+      if (tile < my_tiles) {
+        const int r = tile * 16 + g;
+        if (t == (g >> 1)) {   // this thread holds the diagonal elements (g, g) and (g + 8, g + 8)
+          const float s0 = (g & 1) ? yd[i][0][1] : yd[i][0][0];
+          const float s1 = (g & 1) ? yd[i][1][3] : yd[i][1][2];
+          if (r < rows_valid) a.ny2[(int64_t)b * a.Nld + row0 + r] = s0;
+          if (r + 8 < rows_valid) a.ny2[(int64_t)b * a.Nld + row0 + r + 8] = s1;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int m = 8 * j + 2 * t;
+          if (r < rows_valid) *reinterpret_cast<float2*>(Sg + (int64_t)r * MP + m) = make_float2(acc[i][j][0], acc[i][j][1]);
+          if (r + 8 < rows_valid)
+            *reinterpret_cast<float2*>(Sg + (int64_t)(r + 8) * MP + m) = make_float2(acc[i][j][2], acc[i][j][3]);
+        }
+      }
+    }
+  }
+}
+
 struct WidePlan {
   int MP, tiles_per_cta, nsplit, dsplit, ybox, nybox, tpw, nwarps, grid, ring, kt;
   size_t smem;
@@ -550,6 +731,72 @@ int launch_ot_wide_grad(const OtWideGradArgs& g, cudaStream_t st) {
     case 322: return launch_cfg<32, 2>(tx, ty, tdx, tdy, a, p, st);
     case 641: return launch_cfg<64, 1>(tx, ty, tdx, tdy, a, p, st);
     default: return launch_cfg<64, 2>(tx, ty, tdx, tdy, a, p, st);
+  }
+}
+
+namespace {
+struct WideCostPlan {
+  int MP, tiles_per_cta, nsplit, ybox, nybox, tpw, nwarps, grid, ring;
+  size_t smem;
+};
+bool plan_wide_cost(int B, int M, int N, int D, WideCostPlan* p) {
+  if (M < 1 || M > 64 || N < 1 || N > 1024 || D < kSlabCols || D % kSlabCols != 0) return false;
+  p->MP = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
+  const int ntiles = (N + 15) / 16;
+  const int cap = 20;   // two tiles per warp on at most 10 tile warps (+ the producer): 352 threads, no spills at MP = 64
+  p->nsplit = (ntiles + cap - 1) / cap;
+  p->tiles_per_cta = (ntiles + p->nsplit - 1) / p->nsplit;
+  const int rows = p->tiles_per_cta * 16;
+  const size_t stage = (size_t)(p->MP + rows) * kRowB;
+  const size_t budget = rows >= 128 ? 226 * 1024 : 72 * 1024;
+  p->ring = (int)std::min<size_t>(kMaxRing, (budget - 1024 - 256) / stage);
+  if (p->ring < 3) return false;
+  p->smem = (size_t)p->ring * stage + 256 + 1024;
+  if (rows <= 256) { p->ybox = rows; p->nybox = 1; }
+  else { p->ybox = rows / 2; p->nybox = 2; }
+  p->tpw = p->tiles_per_cta > 16 ? 2 : 1;
+  p->nwarps = std::max(4, (p->tiles_per_cta + p->tpw - 1) / p->tpw);
+  const int threads = (p->nwarps + 1) * 32;
+  int ctas_per_sm = std::max(1, std::min((int)((227 * 1024) / p->smem), 2048 / threads));
+  ctas_per_sm = std::min(ctas_per_sm, 3);
+  p->grid = (int)std::min<int64_t>((int64_t)B * p->nsplit, (int64_t)num_sms() * ctas_per_sm);
+  return true;
+}
+template <int MP, int TPW>
+int launch_cost_cfg(const CUtensorMap& tx, const CUtensorMap& ty, const WideCostParams& a, const WideCostPlan& p,
+                    cudaStream_t st) {
+  auto kern = ot_wide_cost_kernel<MP, TPW>;
+  CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  kern<<<p.grid, (p.nwarps + 1) * 32, p.smem, st>>>(tx, ty, a);
+  CE_LAUNCH_CHECK();
+  return CE_OK;
+}
+}  // namespace
+
+bool ot_wide_cost_supported(int M, int N, int D, int dtype) {
+  static const bool on = [] { const char* e = getenv("CE_OT_WIDE_COST"); return e == nullptr || atoi(e) != 0; }();
+  WideCostPlan p;
+  return on && dtype == CE_BF16 && plan_wide_cost(1, M, N, D, &p);
+}
+
+int launch_ot_wide_cost(const OtWideCostArgs& g, cudaStream_t st) {
+  WideCostPlan p;
+  if (!plan_wide_cost(g.B, g.M, g.N, g.D, &p)) return fail(CE_ERR_SHAPE, "OT wide cost: unsupported shape");
+  CUtensorMap tx, ty;
+  CE_TRY(make_tmap3d_bf16(&tx, g.txt, g.D, g.M, g.B, g.D, g.txt_bs, kSlabCols, p.MP));
+  CE_TRY(make_tmap3d_bf16(&ty, g.img, g.D, g.N, g.B, g.D, g.img_bs, kSlabCols, p.ybox));
+  WideCostParams a{};
+  a.B = g.B; a.M = g.M; a.N = g.N; a.D = g.D;
+  a.tiles_per_cta = p.tiles_per_cta; a.nsplit = p.nsplit; a.nslab = g.D / kSlabCols;
+  a.ybox = p.ybox; a.nybox = p.nybox; a.ring = p.ring;
+  a.S = g.S; a.nx2 = g.nx2; a.ny2 = g.ny2; a.Nld = g.Nld;
+  switch (p.MP * 10 + p.tpw) {
+    case 161: return launch_cost_cfg<16, 1>(tx, ty, a, p, st);
+    case 162: return launch_cost_cfg<16, 2>(tx, ty, a, p, st);
+    case 321: return launch_cost_cfg<32, 1>(tx, ty, a, p, st);
+    case 322: return launch_cost_cfg<32, 2>(tx, ty, a, p, st);
+    case 641: return launch_cost_cfg<64, 1>(tx, ty, a, p, st);
+    default: return launch_cost_cfg<64, 2>(tx, ty, a, p, st);
   }
 }
 
