@@ -388,8 +388,10 @@ __device__ __forceinline__ float frcp(float x) {
 // SCHEME 1: warp 0 sums them and publishes sigma (2 barriers / iteration, fewer instructions)
 // ASM: keep the kernel matrix A in (dynamic) shared memory instead of registers -- for plans too large
 // for 2 x RPT x 4 registers per thread (64 x 577).
-template <int MP, int RPT, int G, int MINB = 1, int SCHEME = 0, bool ASM = false>
-__global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(IpotArgs a) {
+// ridx / nvalid (optional): compacted list of the sample's valid image rows -- slot k of the thread layout then
+// works on row ridx[k]; padded rows are not visited at all (their W rows and ay are zero-filled at the end).
+template <int MP, int RPT, int G, int SCHEME = 0, bool ASM = false, bool RAGGED = false>
+__device__ __forceinline__ void ipot_body(const IpotArgs& a, const int* ridx, int nvalid) {
   extern __shared__ __align__(16) float s_A[];     // [RPT*RP][MP] when ASM
   constexpr int TC = MP / 4;
   constexpr int RP = G / TC;
@@ -411,6 +413,11 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(Ipot
   const int tc = gt % TC, tr = gt / TC;
   const int m0 = tc * 4;
   auto group_sync = [&]() { if constexpr (G == 32) __syncwarp(); else __syncthreads(); };
+  auto row_of = [&](int i) {                     // image row of this thread's pass i (a.N: none)
+    const int k = tr + i * RP;
+    if constexpr (!RAGGED) return k;
+    else return k < nvalid ? ridx[k] : a.N;
+  };
 
   // ---- masks, lengths, inverse norms -------------------------------------------------------
   float rx[4], xg[4];
@@ -427,13 +434,13 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(Ipot
   float ycount = 0.f;
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
-    int n = tr + i * RP;
+    int n = row_of(i);
     bool pad = n >= a.N || node_is_pad(a.img_mask, a.mask_kind, (int64_t)bb * a.img_ms + n);
     ypad |= (pad ? 1u : 0u) << i;
     if (tc == 0 && !pad) ycount += 1.f;
   }
   auto row_inv_norm = [&](int i) {
-    int n = tr + i * RP;
+    int n = row_of(i);
     float n2 = n < a.N ? a.ny2[(int64_t)bb * a.Nld + n] : 1.f;
     return 1.f / fmaxf(sqrtf(n2), a.eps);
   };
@@ -462,7 +469,7 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(Ipot
   const float nib = -1.f / a.beta;
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
-    int n = tr + i * RP;
+    int n = row_of(i);
     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < a.N) s4 = *reinterpret_cast<const float4*>(Sg + (int64_t)n * MP + m0);
     const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
@@ -620,7 +627,7 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(Ipot
   float px[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
-    int n = tr + i * RP;
+    int n = row_of(i);
     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < a.N) s4 = *reinterpret_cast<const float4*>(Sg + (int64_t)n * MP + m0);
     const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
@@ -686,7 +693,66 @@ __global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(Ipot
       if (lane == 0) a.dist[b] = dsum;
     }
   }
+  if (RAGGED && live) {   // padded rows were not visited: their plan rows and ay are zero
+    for (int n = gt; n < a.N; n += G) {
+      if (node_is_pad(a.img_mask, a.mask_kind, (int64_t)b * a.img_ms + n)) {
+        float4* wrow = reinterpret_cast<float4*>(Sg + (int64_t)n * MP);
+#pragma unroll
+        for (int j = 0; j < MP / 4; ++j) wrow[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        a.ny2[(int64_t)b * a.Nld + n] = 0.f;
+      }
+    }
+  }
 }
+
+template <int MP, int RPT, int G, int MINB = 1, int SCHEME = 0, bool ASM = false>
+__global__ void __launch_bounds__((G < 256 ? 256 : G), MINB) ot_ipot_kernel(const __grid_constant__ IpotArgs a) {
+  ipot_body<MP, RPT, G, SCHEME, ASM>(a, nullptr, 0);
+}
+
+// Ragged node sets (the reference pads them, dataset_voa.py:566-577): one CTA per sample compacts the valid image
+// rows and runs the solver body sized for THEM -- a sample with 60 of 257 rows valid takes the 2-pass body, not the
+// 9-pass one.  Same arithmetic per valid row; padded rows cost nothing.
+template <int MP>
+__global__ void __launch_bounds__(256, 2) ot_ipot_ragged_kernel(const __grid_constant__ IpotArgs a) {
+  constexpr int RP = 256 / (MP / 4);
+  constexpr int kSlots = 9 * RP;
+  __shared__ int s_idx[kSlots];
+  __shared__ int s_wcnt[(kSlots + 255) / 256][8];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int b = blockIdx.x;
+  constexpr int NH = (kSlots + 255) / 256;
+  int pos[NH];
+  bool val[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const int n = h * 256 + tid;
+    val[h] = n < a.N && !node_is_pad(a.img_mask, a.mask_kind, (int64_t)b * a.img_ms + n);
+    const uint32_t bal = __ballot_sync(0xffffffffu, val[h]);
+    pos[h] = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) s_wcnt[h][wrp] = __popc(bal);
+  }
+  __syncthreads();
+  int nvalid = 0;
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    int before = nvalid;
+    for (int ww = 0; ww < 8; ++ww) {
+      const int cnt = s_wcnt[h][ww];
+      if (ww < wrp) before += cnt;
+      nvalid += cnt;
+    }
+    if (val[h]) s_idx[before + pos[h]] = h * 256 + tid;
+  }
+  __syncthreads();
+  const int np = (nvalid + RP - 1) / RP;
+  if (np <= 1) ipot_body<MP, 1, 256, 0, false, true>(a, s_idx, nvalid);
+  else if (np <= 2) ipot_body<MP, 2, 256, 0, false, true>(a, s_idx, nvalid);
+  else if (np <= 4) ipot_body<MP, 4, 256, 0, false, true>(a, s_idx, nvalid);
+  else if (np <= 7) ipot_body<MP, 7, 256, 0, false, true>(a, s_idx, nvalid);
+  else ipot_body<MP, 9, 256, 0, false, true>(a, s_idx, nvalid);
+}
+
 
 // Fallback solver for shapes whose plan does not fit the register-resident kernel: same maths,
 // kernel matrix and plan live in a global scratch (L2-resident), one CTA per sample.
@@ -1291,6 +1357,10 @@ int launch_ipot_mp(const IpotArgs& a, int N, cudaStream_t st, bool* handled) {
 #define CE_IPOT_CASE(COND, R, G, ...) \
   if (COND <= R) { ot_ipot_kernel<MP, R, G, ##__VA_ARGS__><<<(G == 32 ? (a.B + 7) / 8 : a.B), (G < 256 ? 256 : G), 0, st>>>(a); return CE_OK; }
   CE_IPOT_CASE(rptw, 2, 32, 2) CE_IPOT_CASE(rptw, 4, 32, 2) CE_IPOT_CASE(rptw, 7, 32, 2) CE_IPOT_CASE(rptw, 10, 32)
+  {   // CE_OT_RAGGED=0 (tuning aid): every sample runs the body sized for N
+    static const bool ragged_on = [] { const char* e = getenv("CE_OT_RAGGED"); return e == nullptr || atoi(e) != 0; }();
+    if (ragged_on && rpt256 >= 2 && rpt256 <= 9) { ot_ipot_ragged_kernel<MP><<<a.B, 256, 0, st>>>(a); return CE_OK; }
+  }
   CE_IPOT_CASE(rpt256, 1, 256) CE_IPOT_CASE(rpt256, 2, 256) CE_IPOT_CASE(rpt256, 4, 256)
   // (measured at c4 and dropped: 512 threads per sample, and the two-barrier SCHEME 1 at either size)
   CE_IPOT_CASE(rpt256, 7, 256, 2, 0) CE_IPOT_CASE(rpt256, 9, 256, 2, 0) CE_IPOT_CASE(rpt256, 13, 256)
