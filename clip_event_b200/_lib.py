@@ -39,6 +39,8 @@ SIGNATURES = {
     "ce_ot_trace": (_i, [_vp, _i, _i, _vp, _vp]),
     "ce_scale_inplace": (_i, [_vp, _i64, _i64, _i64, _i, _vp, _vp]),
     "ce_scale_inplace_same": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
+    "ce_head_losses_cast": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "ce_head_step_scale": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "ce_dense_ce_workspace_bytes": (_sz, [_i]),
     "ce_dense_ce_fwd": (_i, [_vp, _i64, _i64, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "ce_dense_ce_bwd": (_i, [_vp, _i64, _i64, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i64, _vp, _vp]),

@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libclip_event_b200.so")
-SOURCES = ["api_common.cu", "ot_kernels.cu", "ot_fused.cu", "ot_stream.cu", "ot_wide.cu", "dense_ce.cu", "contrastive.cu"]
+SOURCES = ["api_common.cu", "ot_kernels.cu", "ot_fused.cu", "ot_stream.cu", "ot_wide.cu", "dense_ce.cu", "head_step.cu", "contrastive.cu"]
 HEADERS = ["ce_common.cuh", "umma_gemm.cuh", "ot_fused.cuh", os.path.join("..", "..", "include", "clip_event_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -422,7 +422,7 @@ class _GlobalLossHeadStep(torch.autograd.Function):
         # 4. gradients of (loss_i + loss_t) for unit upstream gradients
         dimg = dtxt = dls_tot = None
         if need_c:
-            one = torch.ones(1, dtype=torch.float32, device=dev)
+            one = F_.unit_gradient(dev)
             g = one * world if ddp_average else one
             dimg_buf, dls_buf = ex.grad_buffers(R, D, dev)
             extra = () if dimg_buf is None else (dimg_buf, dls_buf)
@@ -447,33 +447,27 @@ class _GlobalLossHeadStep(torch.autograd.Function):
         dimg, dtxt, dls, detxt, dobj, _ = ctx.stash
         ctx.stash = None
         out = [None] * 14
-        if dimg is not None and (g_i is not None or g_t is not None):
-            if g_i is None or g_t is None:
-                raise RuntimeError("loss_i and loss_t must be back-propagated together on the fused step")
-            ls_dtype, ls_shape = ctx.ls_meta
-            if dimg.is_cuda:   # scale launches that return on the device when the upstream gradient is 1
-                lib = L.load()
-                gi = g_i.detach().to(torch.float32).reshape(1).contiguous()
-                gt = g_t.detach().to(torch.float32).reshape(1).contiguous()
-                for t in (dimg, dtxt, dls):
-                    L.check(lib.ce_scale_inplace_same(t.data_ptr(), t.numel(), L.dtype_code(t.dtype), gi.data_ptr(),
-                                                      gt.data_ptr(), L.stream_ptr()), "sharded loss head step backward")
-            else:
+        use_c = dimg is not None and (g_i is not None or g_t is not None)
+        use_o = detxt is not None and g_ot is not None
+        if use_c and (g_i is None or g_t is None):
+            raise RuntimeError("loss_i and loss_t must be back-propagated together on the fused step")
+        if (use_c and dimg.is_cuda) or (use_o and detxt.is_cuda):
+            # ONE scale launch over every gradient buffer; it returns on the device when the upstream gradients are 1
+            F_.head_step_scale((dimg, dtxt, dls) if use_c else (), (detxt, dobj) if use_o else (),
+                               g_i if use_c else None, g_t if use_c else None, g_ot if use_o else None,
+                               "sharded loss head step backward")
+        else:
+            if use_c:
                 gf, gtf = g_i.detach().float(), g_t.detach().float()
                 g = torch.where(gf == gtf, gf, torch.full_like(gf, float("nan")))
                 dimg, dtxt, dls = (dimg.float() * g).to(dimg.dtype), (dtxt.float() * g).to(dtxt.dtype), dls * g
-            out[0], out[1], out[2] = dimg, dtxt, dls.reshape(ls_shape).to(ls_dtype)
-        if detxt is not None and g_ot is not None:
-            if detxt.is_cuda:
-                lib = L.load()
-                g = g_ot.detach().to(torch.float32).reshape(1).contiguous()
-                for t in (detxt, dobj):
-                    tc = t if t.is_contiguous() else t.contiguous()
-                    L.check(lib.ce_scale_inplace(tc.data_ptr(), 1, tc.numel(), tc.numel(), L.dtype_code(tc.dtype),
-                                                 g.data_ptr(), L.stream_ptr()), "sharded loss head step backward")
-            else:
+            if use_o:
                 g = g_ot.detach().float()
                 detxt, dobj = (detxt.float() * g).to(detxt.dtype), (dobj.float() * g).to(dobj.dtype)
+        if use_c:
+            ls_dtype, ls_shape = ctx.ls_meta
+            out[0], out[1], out[2] = dimg, dtxt, dls.reshape(ls_shape).to(ls_dtype)
+        if use_o:
             out[3], out[4] = detxt, dobj
         return tuple(out)
 

@@ -22,6 +22,57 @@ def _scalar_f32(t: torch.Tensor, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
 
 
+_ONES = {}
+
+
+def unit_gradient(device) -> torch.Tensor:
+    """A device scalar 1.0 (the upstream gradient the eager gradient launches are formed for), made once per device
+    -- not while a CUDA graph is being captured, where a first use would tie the constant to that graph's pool."""
+    if device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+        return torch.ones(1, dtype=torch.float32, device=device)
+    t = _ONES.get(device)
+    if t is None:
+        t = _ONES[device] = torch.ones(1, dtype=torch.float32, device=device)
+        if device.type == "cuda":
+            torch.cuda.current_stream(device).synchronize()     # once: later calls may come from any stream
+    return t
+
+
+def _upstream(g: Optional[torch.Tensor], device):
+    """(tensor kept alive, pointer, dtype code) of an upstream gradient for ce_head_step_scale: read on the device in
+    the dtype autograd delivers it in; anything but an fp32 / bf16 device scalar goes through one cast."""
+    if g is None:
+        return None, 0, L.CE_F32
+    g = g.detach()
+    if g.device != device or g.dtype not in (torch.float32, torch.bfloat16) or g.numel() != 1:
+        g = _scalar_f32(g, device)
+    return g, g.data_ptr(), L.dtype_code(g.dtype)
+
+
+def head_step_scale(contrastive_bufs, ot_bufs, g_i, g_t, g_ot, what: str) -> None:
+    """Every stashed gradient buffer of a one-call loss head step times the upstream gradient of its loss, ONE
+    launch (``ce_head_step_scale``): a no-op on the device under ``sum(loss_dict.values()).backward()``."""
+    import ctypes
+    bufs = [(t, 0) for t in contrastive_bufs if t is not None] + [(t, 1) for t in ot_bufs if t is not None]
+    if not bufs:
+        return
+    if any(not t.is_contiguous() for t, _ in bufs):
+        raise RuntimeError("clip_event_b200 " + what + ": gradient buffers must be contiguous")
+    dev = bufs[0][0].device
+    n = len(bufs)
+    keep_i, p_i, dt_c = _upstream(g_i, dev)
+    keep_t, p_t, dt_t = _upstream(g_t, dev)
+    keep_o, p_o, dt_o = _upstream(g_ot, dev)
+    if keep_i is not None and keep_t is not None and dt_c != dt_t:
+        keep_i, keep_t = _scalar_f32(keep_i, dev), _scalar_f32(keep_t, dev)
+        p_i, p_t, dt_c = keep_i.data_ptr(), keep_t.data_ptr(), L.CE_F32
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t, _ in bufs])
+    counts = (ctypes.c_int64 * n)(*[t.numel() for t, _ in bufs])
+    dts = (ctypes.c_int * n)(*[L.dtype_code(t.dtype) for t, _ in bufs])
+    which = (ctypes.c_int * n)(*[w for _, w in bufs])
+    L.check(L.load().ce_head_step_scale(ptrs, counts, dts, which, n, p_i, p_t, dt_c, p_o, dt_o, L.stream_ptr()), what)
+
+
 def _debug_check_finite(losses: torch.Tensor, what: str) -> None:
     """Index errors come back from the kernels as NaN losses (no host synchronisation on the hot
     path).  With CE_CHECK_INPUTS=1 the losses are read back here and a RuntimeError names the cause,
@@ -231,6 +282,7 @@ class _OtAlignment(torch.autograd.Function):
     The forward launch also produces loss_scale * d(sum dist)/d(inputs) (IPOT is not
     differentiated through, model_ot.py:32,81), so the backward is a scale by the incoming
     gradient -- a no-op launch when that is 1, as it is under ``sum(loss_dict.values()).backward()``.
+    A second backward over a retained graph launches the kernel again on the saved inputs.
     """
 
     @staticmethod
@@ -251,35 +303,12 @@ class _OtAlignment(torch.autograd.Function):
         N = obj_c.shape[1] - slot
         if tm.shape != (B, M) or om.shape != (B, N + slot):
             raise RuntimeError("node masks must be [B,M] and [B,N(+1)]")
-        esz = txt_c.element_size()
-        msz = om.element_size()
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        dev = txt_c.device
-        lib = L.load()
-        nbytes = lib.ce_ot_workspace_bytes(B, M, N, D)
-        if nbytes == 0:
-            raise RuntimeError("clip_event_b200 OT: unsupported node counts M=%d N=%d" % (M, N))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        dist = torch.empty(B, dtype=torch.float32, device=dev)
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
         # both gradients live in one allocation, so the backward is ONE scale launch over it
-        if need_grad:
-            n_t = txt_c.numel()
-            n_t_pad = (n_t + 7) // 8 * 8                     # keeps dobj 16-byte aligned
-            gbuf = torch.empty(n_t_pad + obj_c.numel(), dtype=txt_c.dtype, device=dev)
-            if n_t_pad != n_t:
-                gbuf[n_t:n_t_pad].zero_()
-            dtxt = gbuf[:n_t].view_as(txt_c)
-            dobj = gbuf[n_t_pad:].view_as(obj_c)
-        else:
-            gbuf = dtxt = dobj = None
-        L.check(lib.ce_ot_fwd_bwd(
-            txt_c.data_ptr(), M * D, obj_c.data_ptr() + slot * D * esz, (N + slot) * D,
-            tm.data_ptr(), M, om.data_ptr() + slot * msz, N + slot, kind_t, B, M, N, D, dt,
-            float(beta), int(iters), int(k), float(loss_scale), dist.data_ptr(), loss.data_ptr(),
-            L.ptr(dtxt), 0 if dobj is None else dobj.data_ptr() + slot * D * esz,
-            0 if (dobj is None or not slot) else dobj.data_ptr(), ws.data_ptr(), nbytes, L.stream_ptr()),
-            "OT forward")
+        loss, dist, dtxt, dobj, gbuf, _ = _ot_launch(txt_c, obj_c, tm, om, kind_t, drop_slot0, beta, iters, k, loss_scale,
+                                                     need_grad, L.stream_ptr())
+        # what a second backward (retain_graph=True, as the reference's autograd allows) needs to form the gradients again
+        ctx.replay = (txt_c, obj_c, tm, om, kind_t, drop_slot0, beta, iters, k, loss_scale) if need_grad else None
         ctx.stash = (dtxt, dobj, gbuf)
         ctx.loss_scale = float(loss_scale)
         ctx.consumed = False
@@ -288,14 +317,16 @@ class _OtAlignment(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, g_dist):
-        if ctx.consumed:
-            raise RuntimeError("clip_event_b200 OT: backward through the stashed gradients a second time; "
-                               "run the forward again (retain_graph is not supported on this path)")
-        dtxt, dobj, gbuf = ctx.stash
-        if dtxt is None:
+        if ctx.replay is None:
             return (None,) * 9
-        ctx.consumed = True
-        ctx.stash = (None, None, None)
+        if ctx.consumed:
+            # the stashed gradients went to autograd with the first backward (it may own or have changed them):
+            # launch the kernel again on the saved inputs
+            _, _, dtxt, dobj, gbuf, _ = _ot_launch(*ctx.replay, True, L.stream_ptr())
+        else:
+            dtxt, dobj, gbuf = ctx.stash
+            ctx.consumed = True
+            ctx.stash = (None, None, None)
         dev = dtxt.device
         if g_dist is not None:
             # per-sample upstream gradients (optimal_transport_dist users): general path
@@ -551,7 +582,8 @@ class _LossHeadStep(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, img, txt, logit_scale, etxt, obj, labels_i, labels_t, index_pos, tnum, onum, image_loss):
+    def forward(ctx, img, txt, logit_scale, etxt, obj, labels_i, labels_t, index_pos, tnum, onum, image_loss,
+                cast_losses=False):
         L.require_cuda(img, txt, logit_scale, etxt, obj, tnum, onum)
         if img.dtype != txt.dtype or etxt.dtype != obj.dtype:
             raise RuntimeError("features must share a dtype")
@@ -587,7 +619,7 @@ class _LossHeadStep(torch.autograd.Function):
                                        L.ptr(index_pos), B, BT, P, D, mode, dt, out.data_ptr(), out.data_ptr() + 4,
                                        ws.data_ptr(), nbytes, sp), "contrastive forward")
         if need_c:
-            one = torch.ones(1, dtype=torch.float32, device=dev)
+            one = unit_gradient(dev)
             # dimg | dtxt in one allocation (one scale launch in the backward), dls apart (fp32)
             n_i = img_c.numel()
             n_i_pad = (n_i + 7) // 8 * 8
@@ -602,10 +634,17 @@ class _LossHeadStep(torch.autograd.Function):
         else:
             cbuf = dimg = dtxt = dls = None
         cur.wait_stream(side)           # join: everything below and after sees both chains
-        out[2:3].copy_(loss_ot)
         ctx.stash = (cbuf, dimg, dtxt, dls, gbuf, detxt, dobj)
         ctx.ls_meta = (logit_scale.dtype, logit_scale.shape)
         ctx.set_materialize_grads(False)
+        if cast_losses:
+            # the dtypes the reference's criteria return: the logits' for loss_i / loss_t, the nodes' for loss_ot
+            lc = torch.empty(2, dtype=img_c.dtype, device=dev)
+            lo = torch.empty(1, dtype=etxt_c.dtype, device=dev)
+            L.check(lib.ce_head_losses_cast(out.data_ptr(), out.data_ptr() + 4, loss_ot.data_ptr(), lc.data_ptr(), dt,
+                                            lo.data_ptr(), L.dtype_code(etxt_c.dtype), sp), "loss head step losses")
+            return lc[0], lc[1], lo[0]
+        out[2:3].copy_(loss_ot)
         return out[0], out[1], out[2]
 
     @staticmethod
@@ -615,37 +654,32 @@ class _LossHeadStep(torch.autograd.Function):
                                "(retain_graph is not supported on this path)")
         cbuf, dimg, dtxt, dls, gbuf, detxt, dobj = ctx.stash
         if cbuf is None and gbuf is None:
-            return (None,) * 11
+            return (None,) * 12
         ctx.consumed = True
         ctx.stash = (None,) * 7
-        lib = L.load()
-        out = [None] * 11
-        if cbuf is not None and (g_i is not None or g_t is not None):
-            if g_i is None or g_t is None:
-                raise RuntimeError("clip_event_b200 loss head step: loss_i and loss_t must be back-propagated together "
-                                   "(use CriterionContrastive for a single-sided or weighted loss)")
-            dev = cbuf.device
-            gi, gt = _scalar_f32(g_i, dev), _scalar_f32(g_t, dev)
-            dtc = L.dtype_code(cbuf.dtype)
-            L.check(lib.ce_scale_inplace_same(cbuf.data_ptr(), cbuf.numel(), dtc, gi.data_ptr(), gt.data_ptr(), L.stream_ptr()),
-                    "loss head step backward")
-            L.check(lib.ce_scale_inplace_same(dls.data_ptr(), 1, L.CE_F32, gi.data_ptr(), gt.data_ptr(), L.stream_ptr()),
-                    "loss head step backward")
+        out = [None] * 12
+        use_c = cbuf is not None and (g_i is not None or g_t is not None)
+        use_o = gbuf is not None and g_ot is not None
+        if use_c and (g_i is None or g_t is None):
+            raise RuntimeError("clip_event_b200 loss head step: loss_i and loss_t must be back-propagated together "
+                               "(use CriterionContrastive for a single-sided or weighted loss)")
+        head_step_scale((cbuf, dls) if use_c else (), (gbuf,) if use_o else (), g_i if use_c else None,
+                        g_t if use_c else None, g_ot if use_o else None, "loss head step backward")
+        if use_c:
             ls_dtype, ls_shape = ctx.ls_meta
             out[0], out[1], out[2] = dimg, dtxt, dls.reshape(ls_shape).to(ls_dtype)
-        if gbuf is not None and g_ot is not None:
-            g = _scalar_f32(g_ot, gbuf.device)
-            L.check(lib.ce_scale_inplace(gbuf.data_ptr(), 1, gbuf.numel(), gbuf.numel(), L.dtype_code(gbuf.dtype),
-                                         g.data_ptr(), L.stream_ptr()), "loss head step backward")
+        if use_o:
             out[3], out[4] = detxt, dobj
         return tuple(out)
 
 
 def loss_head_step(image_features, text_features, logit_scale, labels_per_image, labels_per_text, index_pos,
-                   entitytxt_vec, object_vec, entitytxt_num, object_num, image_loss="ce_overbatch"):
-    """(loss_i, loss_t, loss_ot) of the whole loss head in one call; see :class:`_LossHeadStep`."""
+                   entitytxt_vec, object_vec, entitytxt_num, object_num, image_loss="ce_overbatch", cast_losses=False):
+    """(loss_i, loss_t, loss_ot) of the whole loss head in one call; see :class:`_LossHeadStep`.  fp32 losses, or
+    (``cast_losses``) the dtypes the reference's criteria return them in, cast inside the call."""
     return _LossHeadStep.apply(image_features, text_features, logit_scale, entitytxt_vec, object_vec,
-                               labels_per_image, labels_per_text, index_pos, entitytxt_num, object_num, image_loss)
+                               labels_per_image, labels_per_text, index_pos, entitytxt_num, object_num, image_loss,
+                               cast_losses)
 
 
 # --------------------------------------------------------------------------------------------

@@ -309,7 +309,10 @@ class LossHeadStep(nn.Module):
                                                   object_vec, entitytxt_num, object_num, group=pg,
                                                   ddp_average=self.ddp_average)
         else:
+            # the losses come back in the dtypes the reference's criteria return them in (cast inside the call)
             li, lt, lo = F_.loss_head_step(image_features, text_features, ls, labels_per_image, labels_per_text,
-                                           index_pos, entitytxt_vec, object_vec, entitytxt_num, object_num)
+                                           index_pos, entitytxt_vec, object_vec, entitytxt_num, object_num,
+                                           cast_losses=True)
+            return {"loss_i": li, "loss_t": lt, "loss_ot": lo}
         dt = image_features.dtype
         return {"loss_i": li.to(dt), "loss_t": lt.to(dt), "loss_ot": lo.to(entitytxt_vec.dtype)}

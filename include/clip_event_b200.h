@@ -253,6 +253,24 @@ int ce_scale_inplace(void* x, int64_t rows, int64_t row_len, int64_t row_stride,
 int ce_scale_inplace_same(void* x, int64_t n, int dtype, const float* g, const float* g_same,
                           ce_stream_t stream);
 
+/* The glue either side of the one-call loss head (engine.py:48-67 forms the losses, :67 sums them, :88
+ * back-propagates the sum), one launch each:
+ *   ce_head_losses_cast   out_c[0], out_c[1] = *loss_i, *loss_t in `dtype_c`; out_o[0] = *loss_ot in `dtype_o`
+ *                         -- the dtypes the reference's criteria return (model_clip.py:646-659 follow the logits,
+ *                         :699-707 the node embeddings); a NULL loss pointer is skipped.
+ *   ce_head_step_scale    bufs[k] (counts[k] elements of dtypes[k]) *= the upstream gradient of its loss:
+ *                         which[k] == 0 -> *g_i, and every element becomes NaN if *g_t != *g_i (the
+ *                         contrastive gradients were formed for equal upstream gradients); which[k] == 1 ->
+ *                         *g_ot.  The upstream gradients are device scalars of g_dtype_c / g_dtype_o (what
+ *                         autograd delivers for losses of those dtypes); a NULL gradient leaves its buffers
+ *                         alone.  Returns immediately on the device when every gradient is 1.  The arrays are
+ *                         host arrays read during the call; at most 8 buffers. */
+int ce_head_losses_cast(const float* loss_i, const float* loss_t, const float* loss_ot, void* out_c,
+                        int dtype_c, void* out_o, int dtype_o, ce_stream_t stream);
+int ce_head_step_scale(void* const* bufs, const int64_t* counts, const int* dtypes, const int* which,
+                       int nbuf, const void* g_i, const void* g_t, int g_dtype_c, const void* g_ot,
+                       int g_dtype_o, ce_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * CriterionContrastive on MATERIALISED logits (model_clip.py:633-662): the reference's criterion
  * accepts any logits tensors.  Memory-bound row kernels (one CTA per row, 16-byte loads):

@@ -191,13 +191,18 @@ def test_ot_upstream_gradient_scaling_and_per_sample_path():
     assert rel_err(tg.grad.cpu(), dx_ref) < F32_GRAD and rel_err(og.grad.cpu(), dy_ref) < F32_GRAD
 
 
-def test_ot_second_backward_raises():
-    txt, obj, tnum, onum = syn.ot_inputs(2, 4, 6, 16, 0, "full")
-    tg = txt.cuda().requires_grad_(True)
-    loss, _ = F_.ot_alignment(tg, obj.cuda(), tnum.cuda(), onum.cuda())
+def test_ot_second_backward_over_a_retained_graph():
+    """The reference's autograd allows ``backward(retain_graph=True)`` followed by another backward; the stashed
+    gradients belong to autograd after the first one, so the second launches the kernel again: .grad doubles."""
+    txt, obj, tnum, onum = syn.ot_inputs(5, 4, 6, 16, 0, "ragged")
+    tg, og = txt.cuda().requires_grad_(True), obj.cuda().requires_grad_(True)
+    loss, dist = F_.ot_alignment(tg, og, tnum.cuda(), onum.cuda())
     loss.backward(retain_graph=True)
-    with pytest.raises(RuntimeError, match="second time"):
-        loss.backward()
+    g1t, g1o = tg.grad.clone(), og.grad.clone()
+    (3.0 * loss).backward(retain_graph=True)
+    assert rel_err(tg.grad, 4 * g1t) < 1e-6 and rel_err(og.grad, 4 * g1o) < 1e-6
+    dist.sum().backward()                               # per-sample path on the third pass: d(sum dist) = grads / 0.01
+    assert rel_err(tg.grad, 104 * g1t) < 1e-5 and rel_err(og.grad, 104 * g1o) < 1e-5
 
 
 # ------------------------------------------------------------------------------------------

@@ -59,6 +59,26 @@ def main():
                 ok = ok and good
                 print("rank %d %s B=%d T=%d D=%d: %s %s" % (rank, str(dtype)[6:], B, T, D, "OK " if good else "BAD",
                                                          " ".join("%s=%.2e" % kv for kv in errs.items())), flush=True)
+                # the same step through the one-call sharded loss head (what bench.py --gpus N times), with an
+                # upstream gradient of 2 on every loss: one scale launch over all five gradient buffers
+                lv = dict(img=img[lo:hi], txt=txt[lo * T:hi * T], etxt=etxt[lo:hi], obj=obj[lo:hi])
+                lv = {k: v.to(dev).requires_grad_(True) for k, v in lv.items()}
+                ls2 = ls.to(dev).requires_grad_(True)
+                f_i, f_t, f_o = cd.global_loss_head_step(lv["img"], lv["txt"], ls2, li_ if D == 512 else None, lt_, ip_,
+                                                         lv["etxt"], lv["obj"], tnum[lo:hi].to(dev), onum[lo:hi].to(dev))
+                (2.0 * (f_i + f_t + f_o)).backward()
+                torch.cuda.synchronize()
+                e2 = dict(loss_i=abs(f_i.item() - ri.item()) / abs(ri.item()), loss_t=abs(f_t.item() - rt.item()),
+                          loss_ot=abs(f_o.item() - 0.01 * d_ref.sum().item()) / abs(0.01 * d_ref.sum().item()),
+                          dimg=rel(lv["img"].grad, 2 * rdi[lo:hi]), dtxt=rel(lv["txt"].grad, 2 * rdt[lo * T:hi * T]),
+                          dls=abs(ls2.grad.item() - 2 * rdls.item()) / max(1.0, abs(2 * rdls.item())),
+                          detxt=rel(lv["etxt"].grad, 2 * dx_ref[lo:hi]), dobj=rel(lv["obj"].grad[:, 1:], 2 * dy_ref[lo:hi]))
+                good2 = (e2["loss_i"] < lt + 2e-6 and e2["loss_t"] < lt * abs(rt.item()) + (2e-6 if dtype == torch.float32 else 1e-4)
+                         and e2["loss_ot"] < lt and e2["dimg"] < gt and e2["dtxt"] < gt and e2["detxt"] < gt
+                         and e2["dobj"] < gt and e2["dls"] < (1e-4 if dtype == torch.float32 else 1e-2))
+                ok = ok and good2
+                print("rank %d %s B=%d one-call step: %s %s" % (rank, str(dtype)[6:], B, "OK " if good2 else "BAD",
+                                                              " ".join("%s=%.2e" % kv for kv in e2.items())), flush=True)
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.destroy_process_group()
