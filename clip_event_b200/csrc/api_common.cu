@@ -1,6 +1,7 @@
 // Library-wide plumbing: version, thread-local error string, device check, TMA descriptor factory.
 #include <algorithm>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ce_common.cuh"
@@ -30,7 +31,21 @@ void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 static thread_local int g_dev_checked = -1;  // device ordinal that passed the check
 static thread_local int g_sms = 0;
 
+namespace {
+thread_local bool g_pdl_prev_kernel = false;
+// read per launch (not cached): a captured graph keeps the edges it was captured with, so a tool can capture the
+// same step both ways in one process (tools/pdl_check.py)
+bool pdl_enabled() {
+  const char* e = getenv("CE_PDL");
+  return e != nullptr ? e[0] != '0' : true;
+}
+}  // namespace
+bool pdl_use() { return g_pdl_prev_kernel && pdl_enabled(); }
+void pdl_mark() { g_pdl_prev_kernel = true; }
+void pdl_break() { g_pdl_prev_kernel = false; }
+
 int check_device() {
+  pdl_break();   // every API call starts a chain of its own
   // PyTorch runs backward() on its own thread: the driver entry points used for tensor maps need the
   // primary context bound to THAT thread, which only a runtime call that touches the device does
   static thread_local bool ctx_bound = false;

@@ -31,14 +31,63 @@ int num_sms();
 
 void count_launch();  // bumps the per-process kernel-launch counter (ce_debug_launch_count)
 
+// Programmatic dependent launch along a chain of this library's kernels (CE_PDL=0 turns it off).  A kernel
+// launched with CE_LAUNCH_CHAIN carries cudaLaunchAttributeProgrammaticStreamSerialization when the operation
+// before it ON THE SAME API CALL AND STREAM was another CE_LAUNCH_CHAIN kernel: its CTAs become resident while the
+// predecessor drains and sit in griddepcontrol.wait (pdl_wait(), the first statement of every chain kernel) until
+// the predecessor has completed and flushed -- the launch latency between two dependent kernels leaves the
+// critical path, the data dependence stays exactly the stream order.  The chain is per thread and is broken at
+// every API entry (check_device()), by every classic launch (CE_LAUNCH_CHECK) and by CE_MEMSET_ASYNC, so the
+// attribute never follows a non-kernel operation or a kernel that does not begin with pdl_wait().
+bool pdl_use();     // this launch may carry the attribute
+void pdl_mark();    // a chain kernel was just launched
+void pdl_break();   // anything else went into the stream
+
 #define CE_LAUNCH_CHECK()                                                                      \
   do {                                                                                         \
     ::ce::count_launch();                                                                      \
+    ::ce::pdl_break();                                                                         \
     cudaError_t _e = cudaGetLastError();                                                       \
     if (_e != cudaSuccess) {                                                                   \
       ::ce::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
       return (int)_e;                                                                          \
     }                                                                                          \
+  } while (0)
+
+#define CE_MEMSET_ASYNC(ptr, value, bytes, st)                                                 \
+  do {                                                                                         \
+    ::ce::pdl_break();                                                                         \
+    CE_CUDA_TRY(cudaMemsetAsync(ptr, value, bytes, st));                                       \
+  } while (0)
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl_use()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
+// kern(args...) on `st` as a link of the chain described above
+#define CE_LAUNCH_CHAIN(kern, grid, block, smem, st, ...)                                      \
+  do {                                                                                         \
+    cudaError_t _e = ::ce::launch_chain(kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__); \
+    ::ce::count_launch();                                                                      \
+    if (_e != cudaSuccess) {                                                                   \
+      ::ce::pdl_break();                                                                       \
+      ::ce::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                                          \
+    }                                                                                          \
+    ::ce::pdl_mark();                                                                          \
   } while (0)
 
 #define CE_TRY(expr)            \
@@ -73,6 +122,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// First statement of every kernel launched with CE_LAUNCH_CHAIN: returns once the kernels before this one in the
+// stream have completed and their writes are visible (at once when the launch carried no programmatic
+// dependence); then lets the NEXT kernel of the chain take the SMs this one frees as it drains.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -556,6 +556,7 @@ __device__ __forceinline__ void prep_one_row(const void* src, int64_t sr, int r,
 }
 template <int DT>
 __global__ void prep_all_kernel(PrepAllArgs a) {
+  pdl_wait();
   const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wi == 0 && lane == 0) { a.status[0] = 0; a.status[1] = 0; }   // consumed by later launches of this stream
   if (wi < a.R) {
@@ -718,6 +719,7 @@ __device__ __forceinline__ double block_sum_double(double s, double* sh) {
 // last reduces the text-side items in a fixed order (and, on one GPU, emits both losses): three
 // launches of the chain in one.
 __global__ void __launch_bounds__(256) fwd_items_kernel(ItemArgs a) {
+  pdl_wait();
   int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int err = 0;
@@ -825,6 +827,7 @@ template <int DT, int kMaxIter>
 __global__ void __launch_bounds__(256) normalize_bwd_kernel(const void* xin, const float* d, int rows, int D, void* out,
                                      const int* extra_idx, const float* extra,
                                      const float* dls_part, int n_dls, float* dls_out) {
+  pdl_wait();
   using T = typename In<DT>::type;
   constexpr int V = In<DT>::kVec;
   if (blockIdx.x == 0 && dls_out != nullptr) {
@@ -929,11 +932,9 @@ int launch_normalize_bwd(const void* x, const float* d, int rows, int D, void* o
   const int per_iter = 32 * In<DT>::kVec;
   const int iters = (D + per_iter - 1) / per_iter;
   const int blocks = (int)(((int64_t)rows * 32 + 255) / 256);
-  if (iters <= 1) normalize_bwd_kernel<DT, 1><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra, dls_part, n_dls, dls_out);
-  else if (iters == 2) normalize_bwd_kernel<DT, 2><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra, dls_part, n_dls, dls_out);
-  else if (iters == 3) normalize_bwd_kernel<DT, 3><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra, dls_part, n_dls, dls_out);
-  else normalize_bwd_kernel<DT, 4><<<blocks, 256, 0, st>>>(x, d, rows, D, out, extra_idx, extra, dls_part, n_dls, dls_out);
-  CE_LAUNCH_CHECK();
+  auto kern = iters <= 1 ? normalize_bwd_kernel<DT, 1> : iters == 2 ? normalize_bwd_kernel<DT, 2>
+            : iters == 3 ? normalize_bwd_kernel<DT, 3> : normalize_bwd_kernel<DT, 4>;
+  CE_LAUNCH_CHAIN(kern, blocks, 256, 0, st, x, d, rows, D, out, extra_idx, extra, dls_part, n_dls, dls_out);
   return CE_OK;
 }
 
@@ -953,6 +954,7 @@ struct BwdPrepArgs {
 // of the row.  On the recompute path (temperature too high for stored exponentials) the scales are |row| and
 // the copies are plain, so that the gradient GEMMs that follow are the same launches on either path.
 __global__ void bwd_prep_kernel(BwdPrepArgs a) {
+  pdl_wait();
   const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wi >= a.R + a.P) return;
   const bool is_img = wi < a.R;
@@ -1001,6 +1003,7 @@ struct BwdFixArgs {
 // Two launches (side 0: images, side 1: positives): both add into dI^ rows, and a fixed order between the two keeps
 // the result reproducible run to run (within a side a row has one contributor unless labels repeat).
 __global__ void bwd_onehot_kernel(BwdFixArgs a, int side) {
+  pdl_wait();
   if (!stored_exp_on(a.ls)) return;
   const int lane = threadIdx.x & 31;
   const int wi = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + (side ? a.R : 0);
@@ -1038,6 +1041,7 @@ __global__ void bwd_onehot_kernel(BwdFixArgs a, int side) {
 // block partials in base-2 units (the chain's last kernel sums them and multiplies by ln 2).
 __global__ void __launch_bounds__(256) bwd_dls_dot_kernel(const void* img, const float* rinv_i, const float* dimg_hat,
                                                           const float* ls, int R, int D, float* part) {
+  pdl_wait();
   __shared__ float sh[8];
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   float dot = 0.f;
@@ -1221,8 +1225,7 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     pa.lab_logit_i = w.lab_logit_i; pa.lab_logit_t = w.lab_logit_t;
     pa.status = w.status; pa.label_hi = label_hi;
     const int64_t warps = (int64_t)R + C + P;
-    prep_all_kernel<DT><<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(pa);
-    CE_LAUNCH_CHECK();
+    CE_LAUNCH_CHAIN(prep_all_kernel<DT>, (int)((warps * 32 + 255) / 256), 256, 0, st, pa);
   }
   GemmOperand oi = operand<DT>(img, w.img_p, R, D, 0);
   GemmOperand ot = operand<DT>(txt, w.txt_p, C, D, 0);
@@ -1273,8 +1276,7 @@ int fwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
   ia.col_pos = w.col_pos; ia.lse2_col = w.lse2_col; ia.item_t = w.item_t; ia.image_side = mode == 0 ? 1 : 0;
   ia.status = w.status; ia.sums = sums; ia.lse2_row = w.lse2_row; ia.loss_i = loss_i; ia.loss_t = loss_t;
   int blocks = ((R + P) * 32 + 255) / 256;
-  fwd_items_kernel<<<blocks, 256, 0, st>>>(ia);
-  CE_LAUNCH_CHECK();
+  CE_LAUNCH_CHAIN(fwd_items_kernel, blocks, 256, 0, st, ia);
   return CE_OK;
 }
 
@@ -1294,7 +1296,7 @@ int plain_gemm_bn(const GemmOperand& A, const GemmOperand& B, int K, float* out,
   // with the length of the chain (measured 8.6e-5 relative on d image at K = 36864).  Bound each
   // chain to 2048 reduction elements; the partial sums meet in round-to-nearest red.adds.
   if (TF) splits = std::max(splits, std::min(16, (kblk + 63) / 64));
-  if (splits > 1 && !accumulate) CE_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)A.rows * ldo, st));
+  if (splits > 1 && !accumulate) CE_MEMSET_ASYNC(out, 0, sizeof(float) * (size_t)A.rows * ldo, st);
   // accumulate with red.add: a read-modify-write of the thread-per-row tile is 4x slower (measured)
   typename EpiStore<BN>::Params ep{out, ldo, rowscale, nullptr, ls, (splits > 1 || accumulate) ? 1 : 0, A.rows, B.rows};
   return launch_gemm<TF, BN, EpiStore<BN>, CG>(A, B, K, splits, ep, st);
@@ -1339,15 +1341,14 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
   const void* pos_b = w.pos_p[0];       // B operand of Gt^t pos
   if (stored) {
     // the gradient epilogues return at once when the forward stored E: their partials must read as zero
-    CE_CUDA_TRY(cudaMemsetAsync(w.dls_part, 0, sizeof(float) * (size_t)(w.tiles_g + w.tiles_gt) * 8, st));
+    CE_MEMSET_ASYNC(w.dls_part, 0, sizeof(float) * (size_t)(w.tiles_g + w.tiles_gt) * 8, st);
     BwdPrepArgs pa{};
     pa.img = img; pa.pos = w.pos_p[0]; pa.ls = ls; pa.g_i = g_i; pa.g_t = g_t;
     pa.inv_Ri = 1.f / (float)R_total; pa.inv_Pt = 1.f / (float)P_total;
     pa.lse2_row = w.lse2_row; pa.lse2_col = w.lse2_col; pa.rinv_i = w.rinv_i; pa.norm_i = w.norm_i;
     pa.rinv_p = w.rinv_p; pa.norm_p = w.norm_p; pa.rs_i = w.rs_i; pa.rs_p = w.rs_p;
     pa.img_s = w.img_s; pa.pos_s = w.pos_s; pa.R = R; pa.P = P; pa.D = D;
-    bwd_prep_kernel<<<((R + P) * 32 + 255) / 256, 256, 0, st>>>(pa);
-    CE_LAUNCH_CHECK();
+    CE_LAUNCH_CHAIN(bwd_prep_kernel, ((R + P) * 32 + 255) / 256, 256, 0, st, pa);
     rs_i = w.rs_i; rs_p = w.rs_p; img_b = w.img_s; pos_b = w.pos_s;
   }
   if (mode == 0) {  // image side: rows = images, columns = local descriptions
@@ -1358,8 +1359,8 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     const GemmOut go{w.G[0], R, (int)w.ldg, w.ldg};
     CE_TRY((launch_gemm_auto<TF, BN, EpiGrad<BN, TF>>(2, oi, ot, D, ep, st, TF ? nullptr : &go)));
   } else {          // over-instance image side: direct kernel, writes d I^ (local rows) and d T^
-    CE_CUDA_TRY(cudaMemsetAsync(w.dls_part, 0, sizeof(float) * (size_t)w.tiles_g * 8, st));
-    CE_CUDA_TRY(cudaMemsetAsync(dimg_hat_part, 0, sizeof(float) * (size_t)R * D, st));
+    CE_MEMSET_ASYNC(w.dls_part, 0, sizeof(float) * (size_t)w.tiles_g * 8, st);
+    CE_MEMSET_ASYNC(dimg_hat_part, 0, sizeof(float) * (size_t)R * D, st);
     InstArgs ia{};
     ia.img = img; ia.txt = txt; ia.logit_scale = ls; ia.labels = labels_i_v; ia.rinv_i = w.rinv_i;
     ia.rinv_t = w.rinv_t; ia.b = C / T; ia.T = T; ia.D = D; ia.mode = mode; ia.row_offset = row_offset;
@@ -1399,12 +1400,10 @@ int bwd_partial_impl(const void* img, const void* txt, const float* ls, const vo
     fa.rinv_i = w.rinv_i; fa.rinv_t = w.rinv_t; fa.rinv_p = w.rinv_p; fa.lab_local = w.lab_local; fa.lab_t = w.lab_t;
     fa.lab_logit_i = w.lab_logit_i; fa.lab_logit_t = w.lab_logit_t; fa.lse2_row = w.lse2_row; fa.lse2_col = w.lse2_col;
     fa.dimg_hat = dimg_hat_part; fa.dtxt_hat = w.dtxt_hat; fa.dpos_hat = w.dpos_hat; fa.R = R; fa.P = P; fa.D = D;
-    bwd_onehot_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(fa, 0);
-    bwd_onehot_kernel<<<(P * 32 + 255) / 256, 256, 0, st>>>(fa, 1);
-    CE_LAUNCH_CHECK();
-    bwd_dls_dot_kernel<<<dot_blocks, 256, 0, st>>>(img, w.rinv_i, dimg_hat_part, ls, R, D,
-                                                   w.dls_part + (size_t)(w.tiles_g + w.tiles_gt) * 8);
-    CE_LAUNCH_CHECK();
+    CE_LAUNCH_CHAIN(bwd_onehot_kernel, (R * 32 + 255) / 256, 256, 0, st, fa, 0);
+    CE_LAUNCH_CHAIN(bwd_onehot_kernel, (P * 32 + 255) / 256, 256, 0, st, fa, 1);
+    CE_LAUNCH_CHAIN(bwd_dls_dot_kernel, dot_blocks, 256, 0, st, img, w.rinv_i, dimg_hat_part, ls, R, D,
+                    w.dls_part + (size_t)(w.tiles_g + w.tiles_gt) * 8);
   }
   CE_TRY((launch_normalize_bwd<DT>(txt, w.dtxt_hat, C, D, dtxt, w.col_pos, w.dpos_hat, st, w.dls_part, n_dls, dls_out)));
   return CE_OK;
@@ -1704,8 +1703,8 @@ int proj_bwd_impl(const void* hidden, int64_t sample_stride, const int64_t* toke
   // dy [rows, W] = dfeat [rows, K = D] x proj^t: proj is [N = W, K = D] row-major, a K-major B operand
   CE_TRY((plain_gemm<TF>(operand<DT>(dfeat, w.df, rows, D, 0), operand<DT>(proj, w.pj, W, D, 0), D, w.acc, W, nullptr, nullptr, false, st)));
   if (ln_w != nullptr) {
-    CE_CUDA_TRY(cudaMemsetAsync(dln_w, 0, sizeof(float) * W, st));
-    CE_CUDA_TRY(cudaMemsetAsync(dln_b, 0, sizeof(float) * W, st));
+    CE_MEMSET_ASYNC(dln_w, 0, sizeof(float) * W, st);
+    CE_MEMSET_ASYNC(dln_b, 0, sizeof(float) * W, st);
   }
   proj_ln_bwd_kernel<DT><<<(rows * 32 + 255) / 256, 256, 0, st>>>(hidden, sample_stride, token, ln_w, w.mu, w.rstd, w.acc, rows, W,
                                                                  dx_rows, dln_w, dln_b);
@@ -1798,7 +1797,7 @@ extern "C" int ce_debug_gemm(const void* A, const void* B, float* C, int M, int 
   GemmOperand oa{}, ob{};
   oa.ptr[0] = A; oa.ptr[1] = A; oa.rows = M; oa.ld = a_mn_major ? M : K; oa.mn_major = a_mn_major;
   ob.ptr[0] = B; ob.ptr[1] = B; ob.rows = N; ob.ld = b_mn_major ? N : K; ob.mn_major = b_mn_major;
-  if (split_k > 1) CE_CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+  if (split_k > 1) CE_MEMSET_ASYNC(C, 0, sizeof(float) * (size_t)M * N, st);
   if (dtype == CE_F32) {
     EpiStore<128>::Params ep{C, N, nullptr, nullptr, nullptr, split_k > 1 ? 1 : 0, M, N};
     return launch_gemm<true, 128, EpiStore<128>>(oa, ob, K, split_k, ep, st);
@@ -1815,7 +1814,7 @@ extern "C" int ce_debug_gemm_pair(const void* A, const void* B, float* C, int M,
   GemmOperand oa{}, ob{};
   oa.ptr[0] = A; oa.ptr[1] = A; oa.rows = M; oa.ld = a_mn_major ? M : K; oa.mn_major = a_mn_major;
   ob.ptr[0] = B; ob.ptr[1] = B; ob.rows = N; ob.ld = b_mn_major ? N : K; ob.mn_major = b_mn_major;
-  if (split_k > 1) CE_CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+  if (split_k > 1) CE_MEMSET_ASYNC(C, 0, sizeof(float) * (size_t)M * N, st);
   EpiStore<256>::Params ep{C, N, nullptr, nullptr, nullptr, split_k > 1 ? 1 : 0, M, N};
   return launch_gemm<false, 256, EpiStore<256>, 2>(oa, ob, K, split_k, ep, st);
 }

@@ -137,7 +137,11 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
   using Cfg = GemmCfg<TF32X3, BN, Epi::kStageBytesPerWarp * 8, CG>;
   // plain pointer arithmetic on the shared array keeps the address space known to the compiler
   // (LDS/STS instead of generic LD/ST in the epilogues)
-  if (Epi::skip_all(ep)) return;   // device-side switch between two paths of a captured launch sequence (grid-uniform)
+  // Device-side switch between two paths of a captured launch sequence (grid-uniform).  It may read only INPUTS of the
+  // API call (logit_scale), which no kernel of the launch chain writes, so it is evaluated ahead of pdl_wait(); a
+  // skipped launch still waits before it exits -- its successor's wait must imply the completion of everything
+  // before it.
+  if (Epi::skip_all(ep)) { pdl_wait(); return; }
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // swizzled TMA / UMMA tiles need 1024-byte alignment
   uint8_t* stage_base = smem;
@@ -185,6 +189,9 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const GemmShape gs, const t
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barriers, TMEM, descriptor prefetch) touches no global data: it overlaps the tail of the
+  // kernel before this one when the launch is programmatic
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -470,16 +477,30 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, int K, int k_splits,
   if (items == 0) return CE_OK;
   auto kern = umma_gemm_kernel<TF32X3, BN, Epi, CG>;
   CE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+  // a link of the programmatic-dependent-launch chain (ce_common.cuh): the kernel begins with pdl_wait()
+  const bool pdl = pdl_use();
   if constexpr (CG == 1) {
     const int workers = items < num_sms() ? items : num_sms();
-    kern<<<workers, kGemmThreads, Cfg::kSmemBytes, st>>>(tm, gs, ep);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(workers);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (pdl) {
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+    }
+    CE_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, gs, ep));
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms() / CG * CG);
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -497,9 +518,15 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, int K, int k_splits,
     }
     const int workers = items < max_pairs ? items : max_pairs;
     cfg.gridDim = dim3(workers * CG);
+    if (pdl) {
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.numAttrs = 2;
+    }
     CE_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, gs, ep));
   }
   CE_LAUNCH_CHECK();
+  pdl_mark();
   return CE_OK;
 }
 

@@ -15,7 +15,8 @@
  *     device memory; its only state is a thread-local error string, the launch counter behind
  *     ce_debug_launch_count() and a few debug switches read once from the environment
  *     (CE_GEMM_PAIR, CE_CTR_STORED, CE_OT_STREAM, CE_OT_FUSED, CE_OT_PARKS / CE_OT_CY / CE_OT_GY, CE_OT_TRACE_PTR --
- *     tuning aids, not configuration);
+ *     tuning aids, not configuration); CE_PDL=0 (read at every launch) turns off the programmatic dependent
+ *     launches between the kernels of one ce_contrastive_* call;
  *   - inputs are assumed finite: the streaming OT kernel re-uses its shared-memory row buffers from sample to
  *     sample and multiplies rows that are not loaded for a sample (padding beyond the node count) by exact
  *     zeros, so a NaN / Inf in one sample can surface in the next sample handled by the same thread block;
