@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call with the round's final evidence: GPU suite, smoke(), bench lines (default c3, c2, c4, reference arm),
-# the ncu launch list of the default bench command and a `--set full` capture of the wide-plan OT gradient kernel.
+# the ncu launch list of the default bench command and a `--set full` capture of one pass of the contrastive kernel chain.
 # A command runs under ncu only after the same command line has exited 0 without it.
 set -x
 cd "$(dirname "$0")/.."
@@ -17,9 +17,9 @@ fi
 timeout 200 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-secondary > gpurun_out/${R}_bench_short.json 2> gpurun_out/${R}_bench_short.err &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${R}_launches_c3.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-secondary > gpurun_out/${R}_ncu_launches_c3.log 2>&1
-timeout 120 python tools/ot_tune.py c4 bf16 > gpurun_out/${R}_ot_tune_c4.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:ot_wide_grad" -s 4 -c 1 \
-    -o gpurun_out/prof_${R}_ot_grad_c4 python tools/ot_tune.py c4 bf16 > gpurun_out/${R}_ncu_ot_grad_c4.log 2>&1
+timeout 120 python tools/con_tune.py c3 bf16 > gpurun_out/${R}_con_tune_c3.log 2>&1 &&
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:umma_gemm|bwd_|normalize_bwd|prep_all|fwd_items" -s 100 -c 18 \
+    -o gpurun_out/prof_${R}_gemm_chain python tools/con_tune.py c3 bf16 > gpurun_out/${R}_ncu_gemm.log 2>&1
 for f in default c2 c4; do python - <<EOF
 import json
 d = json.loads(open("gpurun_out/${R}_bench_$f.json").read().strip().splitlines()[-1])
