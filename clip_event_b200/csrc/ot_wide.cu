@@ -693,10 +693,17 @@ int launch_cfg(const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& 
 
 }  // namespace
 
+// Plans of more than 32 text rows keep the plan in shared memory (no register-resident dx product): up to 14 row
+// tiles the mma.sync kernels of ot_kernels.cu are faster there (c5 sweep, batch 512, 50 iterations: 64 x 197 x 768
+// 517 us against 680 us; from 64 x 257 on the TMA kernels win, 843 against 921 us).  CE_OT_WIDE=2 lifts the gate.
+static bool wide_pays(int M, int N) {
+  static const int mode = [] { const char* e = getenv("CE_OT_WIDE"); return e == nullptr ? 1 : atoi(e); }();
+  return mode == 2 || !((M > 32 && N <= 224) || N <= 64);   // tiny plans (4 row tiles): 84 against 91 us at 16 x 50 x 768
+}
 bool ot_wide_supported(int M, int N, int D, int dtype) {
   static const bool on = [] { const char* e = getenv("CE_OT_WIDE"); return e == nullptr || atoi(e) != 0; }();
   WidePlan p;
-  return on && dtype == CE_BF16 && plan_wide(1, M, N, D, &p);
+  return on && dtype == CE_BF16 && wide_pays(M, N) && plan_wide(1, M, N, D, &p);
 }
 int ot_wide_nsplit(int M, int N, int D) {
   WidePlan p;
@@ -776,7 +783,7 @@ int launch_cost_cfg(const CUtensorMap& tx, const CUtensorMap& ty, const WideCost
 bool ot_wide_cost_supported(int M, int N, int D, int dtype) {
   static const bool on = [] { const char* e = getenv("CE_OT_WIDE_COST"); return e == nullptr || atoi(e) != 0; }();
   WideCostPlan p;
-  return on && dtype == CE_BF16 && plan_wide_cost(1, M, N, D, &p);
+  return on && dtype == CE_BF16 && wide_pays(M, N) && plan_wide_cost(1, M, N, D, &p);
 }
 
 int launch_ot_wide_cost(const OtWideCostArgs& g, cudaStream_t st) {

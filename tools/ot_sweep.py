@@ -1,7 +1,7 @@
 """BASELINE config c5: OT sweep -- text nodes 4-64 x image nodes 50-577, IPOT iterations 10-100, batch 512,
 one B200.  Times ce_ot_fwd_bwd (forward + gradients, CUDA-graph replay, CUDA events) for every cell and
 reports the algorithmic HBM rate 2 (M+N) D e B / t against the measured copy bandwidth.
-python tools/ot_sweep.py [out.json]"""
+python tools/ot_sweep.py [out.json] [bf16|fp32]   (second argument: one dtype only)"""
 import json, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -37,9 +37,15 @@ def time_it(fn, n=10):
 
 
 rows = []
+only = sys.argv[2] if len(sys.argv) > 2 else None
+only_m = int(sys.argv[3]) if len(sys.argv) > 3 else None      # third argument: one text-node count only
 for dt in (torch.bfloat16, torch.float32):
+    if only is not None and only != ("bf16" if dt == torch.bfloat16 else "fp32"):
+        continue
     for D in (512, 768):
         for M in (4, 8, 16, 32, 64):
+            if only_m is not None and M != only_m:
+                continue
             for N in (50, 197, 257, 577):
                 etxt, obj, tnum, onum = syn.ot_inputs(B, M, N, D, 0, "ragged", dtype=dt)
                 etxt, obj, tnum, onum = etxt.cuda(), obj.cuda(), tnum.cuda(), onum.cuda()
