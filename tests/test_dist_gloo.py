@@ -48,8 +48,10 @@ def _worker(rank, world, port, B, T, D, q):
             return orc.alignment_criterion(a, b_, c, d)["loss_ot"], None
         loss_ot = cd.sharded_alignment(e_l, o_l, tnum[lo:hi], onum[lo:hi], ot_fn=ot_fn)
         (2.0 * loss_i + 0.5 * loss_t + loss_ot).backward()
-        q.put((rank, loss_i.item(), loss_t.item(), loss_ot.item(), img_l.grad, txt_l.grad, ls_l.grad,
-               e_l.grad, o_l.grad))
+        # numpy copies, pickled by value: a torch tensor travels as a shared-memory handle that the parent must fetch
+        # from THIS process, which may have exited by then
+        q.put((rank, loss_i.item(), loss_t.item(), loss_ot.item(),
+               *[t.grad.detach().numpy().copy() for t in (img_l, txt_l, ls_l, e_l, o_l)]))
     finally:
         dist.destroy_process_group()
 
