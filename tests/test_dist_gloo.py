@@ -65,9 +65,9 @@ def test_global_contrastive_matches_single_process(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, B, T, D, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = sorted([q.get(timeout=60) for _ in range(world)], key=lambda t: t[0])
+    results = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=120)
         assert p.exitcode == 0
 
     img, txt, ls = syn.contrastive_inputs(B, T, D, 5, "trained")
@@ -148,9 +148,9 @@ def test_ddp_parameter_gradients_match_single_process():
     procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, B, T, D, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = sorted([q.get(timeout=90) for _ in range(world)], key=lambda t: t[0])
+    results = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=120)
         assert p.exitcode == 0
     # single process: the same encoders on the whole batch, reference loss (global mean), autograd
     xi, xt, _ = syn.contrastive_inputs(B, T, 12, 9, "trained")
@@ -207,9 +207,9 @@ def test_global_loss_head_step_matches_single_process():
     procs = [ctx.Process(target=_step_worker, args=(r, world, port, B, T, D, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = sorted([q.get(timeout=90) for _ in range(world)], key=lambda t: t[0])
+    results = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=120)
         assert p.exitcode == 0
     img, txt, ls = syn.contrastive_inputs(B, T, D, 5, "trained")
     lpi, lpt, idx = syn.contrastive_labels(B, T)
