@@ -48,6 +48,8 @@ def test_built_for_sm100a_with_tcgen05_and_tma():
     assert "LDTM" in sass, "tcgen05.ld missing from SASS"
     assert "UTCHMMA.2CTA" in sass, "tcgen05.mma.cta_group::2 (CTA-pair GEMM) missing from SASS"
     assert "UTMASTG" in sass, "TMA stores (gradient-tile epilogue) missing from SASS"
+    # programmatic dependent launch along the contrastive chain: griddepcontrol.wait / .launch_dependents
+    assert "ACQBULK" in sass and "PREEXIT" in sass, "griddepcontrol (programmatic dependent launch) missing from SASS"
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
